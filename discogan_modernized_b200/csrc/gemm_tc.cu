@@ -1,0 +1,664 @@
+// Implicit-GEMM 4x4 stride-2 convolution family on tcgen05 / TMEM, operands fed by TMA (sm_100a).
+//
+// Replaces the cuDNN calls behind nn.Conv2d(ci,co,4,2,1) / nn.ConvTranspose2d(ci,co,4,2,1) forward, dgrad and
+// wgrad (reference model.py:11-31, 84-103, 118-138).
+//
+// Tensors are NHWC bf16.  A conv layer connects a "big" tensor [B,2Hs,2Ws,Cb] and a "small" tensor [B,Hs,Ws,Cs];
+// the PyTorch weight seen as conv weight is W[Cs][Cb][4][4] (for ConvTranspose2d the same layout: [in=Cs][out=Cb]).
+//   DOWN (conv fprop / convT dgrad):  small[b,ho,wo,cs] = sum_{kh,kw,cb} big[b,2ho-1+kh,2wo-1+kw,cb] W[cs][cb][kh][kw]
+//        GEMM M = B*Hs*Ws, N = Cs, K = 16*Cb.  A tiles come straight from `big` through a 5-D TMA map that
+//        splits H and W into (coarse, parity): tap (kh,kw) is a shifted box in one parity plane, zero-filled by
+//        TMA outside the image (padding=1).  B = packed weights Wd[Cs][tap][Cb].
+//   UP   (conv dgrad / convT fprop):  big[b,2i+py,2j+px,cb] = sum_{cs, 2x2 taps of that parity} small[...] W
+//        four parity sub-GEMMs, M = B*Hs*Ws, N = Cb, K = 4*Cs, no zero insertion.  B = packed Wu[Cb][tap][Cs].
+//   WGRAD: dW[cs][cb][tap] = sum_{pixels} small[p,cs] * big[p shifted by tap, cb]
+//        GEMM M = Cs, N = Cb per tap, K = pixels; both operands MN-major straight from NHWC via TMA; 8 taps
+//        accumulate side by side in the 512 TMEM columns; split-K partial tiles go to a workspace and a
+//        second kernel reduces them into the fp32 gradient in PyTorch layout.
+//
+// Kernel shape: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM owner), warps 2-5 = epilogue.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;               // bf16 elements = 128 B = one swizzle row
+constexpr int kATileBytes = kBlockM * 128;  // 16 KB
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;           // TMEM columns between the two accumulator stages
+constexpr int kMaxStages = 8;
+
+struct ConvGemmParams {
+  int mode;  // 0 = DOWN, 1 = UP
+  int B, Hm, Wm;  // M-side (small tensor) spatial dims
+  int Wt, Ht, Bt;  // M tile = Wt*Ht*Bt = 128 pixels
+  int tiles_w, tiles_h, tiles_b;
+  int n_tiles, block_n;
+  int Ck;       // channels of the K-side tensor
+  int cpk;      // Ck / 64
+  int k_iters;  // taps * cpk
+  int N;        // output channels
+  int Ho, Wo;   // output spatial dims
+  int num_tiles;
+  int num_stages;
+  bf16* out;
+};
+
+struct TileCoord {
+  int par, nt, b0, h0, w0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int tile) {
+  TileCoord t;
+  t.nt = tile % p.n_tiles;
+  int r = tile / p.n_tiles;
+  int tw = r % p.tiles_w;
+  r /= p.tiles_w;
+  int th = r % p.tiles_h;
+  r /= p.tiles_h;
+  int tb = r % p.tiles_b;
+  t.par = r / p.tiles_b;
+  t.w0 = tw * p.Wt;
+  t.h0 = th * p.Ht;
+  t.b0 = tb * p.Bt;
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int stage_bytes = kATileBytes + p.block_n * 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
+  uint64_t* full_bar = bars;                    // [stages]
+  uint64_t* empty_bar = bars + kMaxStages;      // [stages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int py = t.par >> 1, px = t.par & 1;
+        for (int it = 0; it < p.k_iters; ++it) {
+          const int tap_i = it / p.cpk;
+          const int c0 = (it - tap_i * p.cpk) * kBlockK;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + kATileBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          if (p.mode == 0) {
+            const int kh = tap_i >> 2, kw = tap_i & 3;
+            const int dh = ((kh + 1) >> 1) - 1, ph = (kh + 1) & 1;
+            const int dw = ((kw + 1) >> 1) - 1, pw = (kw + 1) & 1;
+            tma_load_5d(sa, &tmA, &full_bar[stage], pw * p.Ck + c0, t.w0 + dw, ph, t.h0 + dh, t.b0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], tap_i * p.Ck + c0, t.nt * p.block_n);
+          } else {
+            const int th = tap_i >> 1, tw = tap_i & 1;
+            const int kh = py == 0 ? (th ? 3 : 1) : (th ? 2 : 0);
+            const int di = py == 0 ? (th ? -1 : 0) : (th ? 0 : 1);
+            const int kw = px == 0 ? (tw ? 3 : 1) : (tw ? 2 : 0);
+            const int dj = px == 0 ? (tw ? -1 : 0) : (tw ? 0 : 1);
+            tma_load_4d(sa, &tmA, &full_bar[stage], c0, t.w0 + dj, t.h0 + di, t.b0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], (kh * 4 + kw) * p.Ck + c0, t.nt * p.block_n);
+          }
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+        for (int it = 0; it < p.k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = make_sdesc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = make_sdesc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // epilogue: TMEM lane quarter of this warp is (warp % 4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int wl = row % p.Wt;
+      const int hl = (row / p.Wt) % p.Ht;
+      const int bl = row / (p.Wt * p.Ht);
+      const int b = t.b0 + bl;
+      int oy, ox;
+      if (p.mode == 0) {
+        oy = t.h0 + hl;
+        ox = t.w0 + wl;
+      } else {
+        oy = 2 * (t.h0 + hl) + (t.par >> 1);
+        ox = 2 * (t.w0 + wl) + (t.par & 1);
+      }
+      bf16* orow = p.out + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.N + (size_t)t.nt * p.block_n;
+      const bool valid = b < p.B;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+            v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+            v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+            v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+            *reinterpret_cast<uint4*>(orow + c + 8 * j) = v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// WGRAD
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgKC = 32;                       // pixels (GEMM-K) per pipeline stage
+constexpr int kWgBoxBytes = kWgKC * 128;        // one 64-channel x 32-pixel box = 4 KB
+constexpr int kWgStageBytes = 10 * kWgBoxBytes;  // 2 boxes of `small` (128 cs) + 8 taps of `big` (64 cb)
+constexpr int kWgStages = 5;
+
+struct WgradParams {
+  int B, Hs, Ws;
+  int Wt, Ht, Bt;  // K chunk = Wt*Ht*Bt = 32 pixels of the small tensor
+  int chunks_w, chunks_h, chunks_b, total_chunks;
+  int Cs, Cb, m_tiles, n_tiles;
+  int splits, chunks_per_split;
+  float* ws;  // [split][m_tile][n_tile][half][128][512]
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmBig,
+                  const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kWgStages;
+  uint64_t* tfull_bar = bars + 2 * kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int w = blockIdx.x;
+  const int half = w & 1;
+  w >>= 1;
+  const int nt = w % p.n_tiles;
+  const int mt = w / p.n_tiles;
+  const int split = blockIdx.y;
+  const int chunk_begin = split * p.chunks_per_split;
+  const int chunk_end = min(p.total_chunks, chunk_begin + p.chunks_per_split);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmS);
+    tma_prefetch_desc(&tmBig);
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ch = chunk_begin; ch < chunk_end; ++ch) {
+        int r = ch;
+        const int cw = r % p.chunks_w;
+        r /= p.chunks_w;
+        const int chh = r % p.chunks_h;
+        const int cb_ = r / p.chunks_h;
+        const int w0 = cw * p.Wt, h0 = chh * p.Ht, b0 = cb_ * p.Bt;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * kWgStageBytes;
+        uint8_t* sb = sa + 2 * kWgBoxBytes;
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)kWgStageBytes);
+        tma_load_4d(sa, &tmS, &full_bar[stage], mt * 128, w0, h0, b0);
+        tma_load_4d(sa + kWgBoxBytes, &tmS, &full_bar[stage], mt * 128 + 64, w0, h0, b0);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int tap = half * 8 + t;
+          const int kh = tap >> 2, kw = tap & 3;
+          const int dh = ((kh + 1) >> 1) - 1, ph = (kh + 1) & 1;
+          const int dw = ((kw + 1) >> 1) - 1, pw = (kw + 1) & 1;
+          tma_load_5d(sb + t * kWgBoxBytes, &tmBig, &full_bar[stage], pw * p.Cb + nt * 64, w0 + dw, ph, h0 + dh, b0);
+        }
+        if (++stage == kWgStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ch = chunk_begin; ch < chunk_end; ++ch) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kWgStageBytes);
+        const uint32_t sb = sa + 2 * kWgBoxBytes;
+#pragma unroll
+        for (int ks = 0; ks < kWgKC / 16; ++ks) {
+          // MN-major SW128: LBO = distance between 64-wide MN blocks, SBO = distance between 8-row K groups
+          const uint64_t da = make_sdesc_sw128(sa + ks * 2048, kWgBoxBytes, 1024);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const uint64_t db = make_sdesc_sw128(sb + t * kWgBoxBytes + ks * 2048, kWgBoxBytes, 1024);
+            umma_bf16(tmem_base + (uint32_t)(t * 64), da, db, idesc, (ch > chunk_begin || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kWgStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float* dst = p.ws + ((((size_t)split * p.m_tiles + mt) * p.n_tiles + nt) * 2 + half) * (size_t)(128 * 512) +
+                 (size_t)row * 512;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c = 0; c < 512; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        *reinterpret_cast<uint4*>(dst + c + 4 * j) = v;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// dw[cs][cb][tap] = beta*dw + sum_split ws[...]; one thread per (cs, cb, half) writes 8 consecutive taps.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float beta, int Cs, int Cb,
+                                    int m_tiles, int n_tiles, int splits) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)Cs * Cb * 2;
+  if (idx >= total) return;
+  const int cb = (int)(idx % Cb);
+  long long r = idx / Cb;
+  const int half = (int)(r & 1);
+  const int cs = (int)(r >> 1);
+  const int mt = cs >> 7, row = cs & 127, nt = cb >> 6, cbl = cb & 63;
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float* src = ws + ((((size_t)s * m_tiles + mt) * n_tiles + nt) * 2 + half) * (size_t)(128 * 512) +
+                       (size_t)row * 512 + cbl;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] += src[t * 64];
+  }
+  float* d = dw + ((size_t)cs * Cb + cb) * 16 + half * 8;
+  float4 o0, o1;
+  if (beta != 0.f) {
+    o0 = *reinterpret_cast<float4*>(d);
+    o1 = *reinterpret_cast<float4*>(d + 4);
+    o0.x = beta * o0.x + acc[0]; o0.y = beta * o0.y + acc[1]; o0.z = beta * o0.z + acc[2]; o0.w = beta * o0.w + acc[3];
+    o1.x = beta * o1.x + acc[4]; o1.y = beta * o1.y + acc[5]; o1.z = beta * o1.z + acc[6]; o1.w = beta * o1.w + acc[7];
+  } else {
+    o0 = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  *reinterpret_cast<float4*>(d) = o0;
+  *reinterpret_cast<float4*>(d + 4) = o1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+      dg_set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor map, SWIZZLE_128B, zero fill out of bounds. dims/strides fastest-first; strides in elements.
+int make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems,
+             const int* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return DG_ERR_CUDA;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    bdim[i] = (cuuint32_t)box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = (cuuint64_t)strides_elems[i] * 2;
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dg_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %lld %lld %lld, box %d %d %d)", (int)r,
+                 rank, dims[0], dims[1], rank > 2 ? dims[2] : 0, box[0], box[1], rank > 2 ? box[2] : 0);
+    return DG_ERR_CUDA;
+  }
+  return DG_OK;
+}
+
+// parity-split view of an NHWC tensor [B,H,W,C]: dims {2C, W/2, 2, H/2, B}
+int make_parity_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h, int box_b) {
+  long long dims[5] = {2LL * C, W / 2, 2, H / 2, B};
+  long long str[5] = {1, 2LL * C, (long long)W * C, 2LL * W * C, (long long)H * W * C};
+  int box[5] = {64, box_w, 1, box_h, box_b};
+  return make_map(m, base, 5, dims, str, box);
+}
+// plain view of an NHWC tensor [B,H,W,C]: dims {C, W, H, B}
+int make_nhwc_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h, int box_b) {
+  long long dims[4] = {C, W, H, B};
+  long long str[4] = {1, C, (long long)W * C, (long long)H * W * C};
+  int box[4] = {64, box_w, box_h, box_b};
+  return make_map(m, base, 4, dims, str, box);
+}
+int make_weight_map(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
+  long long dims[2] = {cols, rows};
+  long long str[2] = {1, cols};
+  int box[2] = {64, box_rows};
+  return make_map(m, base, 2, dims, str, box);
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// split `pixels` = 128 or 32 over (W, H, B) of a power-of-two image
+void tile_shape(int pixels, int H, int W, int* Wt, int* Ht, int* Bt) {
+  *Wt = W < pixels ? W : pixels;
+  int rest = pixels / *Wt;
+  *Ht = H < rest ? H : rest;
+  *Bt = rest / *Ht;
+}
+
+int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, int B, int Hs, int Ws, int Cs, int Cb,
+                     cudaStream_t stream) {
+  DG_CHECK_ARG(B > 0 && is_pow2(Hs) && is_pow2(Ws), "conv gemm: B=%d Hs=%d Ws=%d must be positive / powers of two", B,
+               Hs, Ws);
+  DG_CHECK_ARG(Cs % 64 == 0 && Cb % 64 == 0 && Cs >= 64 && Cb >= 64, "conv gemm: Cs=%d Cb=%d must be multiples of 64",
+               Cs, Cb);
+  DG_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)wpacked & 15) == 0 && ((uintptr_t)out & 15) == 0,
+               "conv gemm: pointers must be 16-byte aligned");
+  ConvGemmParams p;
+  p.mode = mode;
+  p.B = B;
+  p.Hm = Hs;
+  p.Wm = Ws;
+  tile_shape(kBlockM, Hs, Ws, &p.Wt, &p.Ht, &p.Bt);
+  p.tiles_w = Ws / p.Wt;
+  p.tiles_h = Hs / p.Ht;
+  p.tiles_b = dg_ceil_div(B, p.Bt);
+  const int N = mode == 0 ? Cs : Cb;
+  p.N = N;
+  p.Ck = mode == 0 ? Cb : Cs;
+  p.cpk = p.Ck / 64;
+  p.k_iters = (mode == 0 ? 16 : 4) * p.cpk;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b * (mode == 0 ? 1 : 4);
+  int bn = 64;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    if (N % cands[i]) continue;
+    bn = cands[i];
+    if ((long long)m_tiles * (N / bn) >= num_sms()) break;
+  }
+  p.block_n = bn;
+  p.n_tiles = N / bn;
+  p.num_tiles = m_tiles * p.n_tiles;
+  p.Ho = mode == 0 ? Hs : 2 * Hs;
+  p.Wo = mode == 0 ? Ws : 2 * Ws;
+  p.out = reinterpret_cast<bf16*>(out);
+  const int stage_bytes = kATileBytes + bn * 128;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.num_stages = stages;
+  const int smem_bytes = stages * stage_bytes + 1024 + 256;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (mode == 0) {
+    rc = make_parity_map(&tmA, a, B, 2 * Hs, 2 * Ws, Cb, p.Wt, p.Ht, p.Bt);
+    if (rc) return rc;
+    rc = make_weight_map(&tmB, wpacked, Cs, 16 * Cb, bn);
+  } else {
+    rc = make_nhwc_map(&tmA, a, B, Hs, Ws, Cs, p.Wt, p.Ht, p.Bt);
+    if (rc) return rc;
+    rc = make_weight_map(&tmB, wpacked, Cb, 16 * Cs, bn);
+  }
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      dg_set_error("conv gemm: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+      return DG_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  DG_CHECK_LAUNCH("conv_gemm_kernel");
+  return DG_OK;
+}
+
+void wgrad_plan(int B, int Hs, int Ws, int Cs, int Cb, WgradParams* p) {
+  p->B = B;
+  p->Hs = Hs;
+  p->Ws = Ws;
+  tile_shape(kWgKC, Hs, Ws, &p->Wt, &p->Ht, &p->Bt);
+  p->chunks_w = Ws / p->Wt;
+  p->chunks_h = Hs / p->Ht;
+  p->chunks_b = dg_ceil_div(B, p->Bt);
+  p->total_chunks = p->chunks_w * p->chunks_h * p->chunks_b;
+  p->Cs = Cs;
+  p->Cb = Cb;
+  p->m_tiles = Cs / 128;
+  p->n_tiles = Cb / 64;
+  const int work = p->m_tiles * p->n_tiles * 2;
+  int splits = dg_ceil_div(2 * num_sms(), work);
+  if (splits > p->total_chunks) splits = p->total_chunks;
+  if (splits < 1) splits = 1;
+  p->chunks_per_split = dg_ceil_div(p->total_chunks, splits);
+  p->splits = dg_ceil_div(p->total_chunks, p->chunks_per_split);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dg_conv4x4s2_fprop(const void* x, const void* wd, void* z, int B, int H, int W, int Cb, int Cs,
+                       cudaStream_t stream) {
+  DG_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "fprop: H=%d W=%d must be even", H, W);
+  return launch_conv_gemm(0, x, wd, z, B, H / 2, W / 2, Cs, Cb, stream);
+}
+
+int dg_conv4x4s2_dgrad(const void* dz, const void* wu, void* dx, int B, int Hs, int Ws, int Cs, int Cb,
+                       cudaStream_t stream) {
+  return launch_conv_gemm(1, dz, wu, dx, B, Hs, Ws, Cs, Cb, stream);
+}
+
+size_t dg_conv4x4s2_wgrad_workspace(int B, int Hs, int Ws, int Cs, int Cb) {
+  if (B <= 0 || !is_pow2(Hs) || !is_pow2(Ws) || Cs % 128 || Cb % 64) return 0;
+  WgradParams p;
+  wgrad_plan(B, Hs, Ws, Cs, Cb, &p);
+  return (size_t)p.splits * p.m_tiles * p.n_tiles * 2 * 128 * 512 * sizeof(float);
+}
+
+int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
+                       int Cb, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  DG_CHECK_ARG(B > 0 && is_pow2(Hs) && is_pow2(Ws), "wgrad: B=%d Hs=%d Ws=%d must be positive / powers of two", B, Hs,
+               Ws);
+  DG_CHECK_ARG(Cs % 128 == 0 && Cb % 64 == 0, "wgrad: Cs=%d must be a multiple of 128 and Cb=%d of 64", Cs, Cb);
+  DG_CHECK_ARG(Hs * Ws * 1LL >= 1 && (Hs * Ws >= kWgKC || (kWgKC % (Hs * Ws)) == 0), "wgrad: bad spatial size");
+  WgradParams p;
+  wgrad_plan(B, Hs, Ws, Cs, Cb, &p);
+  const size_t need = (size_t)p.splits * p.m_tiles * p.n_tiles * 2 * 128 * 512 * sizeof(float);
+  DG_CHECK_ARG(ws != nullptr && ws_bytes >= need, "wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
+  DG_CHECK_ARG(((uintptr_t)small & 15) == 0 && ((uintptr_t)big & 15) == 0 && ((uintptr_t)dw & 15) == 0 &&
+                   ((uintptr_t)ws & 15) == 0,
+               "wgrad: pointers must be 16-byte aligned");
+  p.ws = reinterpret_cast<float*>(ws);
+  CUtensorMap tmS, tmBig;
+  int rc = make_nhwc_map(&tmS, small, B, Hs, Ws, Cs, p.Wt, p.Ht, p.Bt);
+  if (rc) return rc;
+  rc = make_parity_map(&tmBig, big, B, 2 * Hs, 2 * Ws, Cb, p.Wt, p.Ht, p.Bt);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      dg_set_error("wgrad: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+      return DG_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int smem_bytes = kWgStages * kWgStageBytes + 1024 + 256;
+  dim3 grid(p.m_tiles * p.n_tiles * 2, p.splits);
+  wgrad_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmS, tmBig, p);
+  DG_CHECK_LAUNCH("wgrad_gemm_kernel");
+  const long long total = (long long)Cs * Cb * 2;
+  wgrad_reduce_kernel<<<dg_ceil_div(total, 256), 256, 0, stream>>>(p.ws, dw, beta, Cs, Cb, p.m_tiles, p.n_tiles,
+                                                                   p.splits);
+  DG_CHECK_LAUNCH("wgrad_reduce_kernel");
+  return DG_OK;
+}
+
+// ConvTranspose2d(ci,co,4,2,1) is the same three GEMMs with the roles swapped (model.py:118-138).
+int dg_convT4x4s2_fprop(const void* x_small, const void* wu, void* y_big, int B, int Hs, int Ws, int Cs, int Cb,
+                        cudaStream_t stream) {
+  return launch_conv_gemm(1, x_small, wu, y_big, B, Hs, Ws, Cs, Cb, stream);
+}
+int dg_convT4x4s2_dgrad(const void* dy_big, const void* wd, void* dx_small, int B, int H, int W, int Cb, int Cs,
+                        cudaStream_t stream) {
+  return dg_conv4x4s2_fprop(dy_big, wd, dx_small, B, H, W, Cb, Cs, stream);
+}
+int dg_convT4x4s2_wgrad(const void* x_small, const void* dy_big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
+                        int Cb, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  return dg_conv4x4s2_wgrad(x_small, dy_big, dw, beta, B, Hs, Ws, Cs, Cb, ws, ws_bytes, stream);
+}
+
+}  // extern "C"

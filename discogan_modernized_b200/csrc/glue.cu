@@ -1,0 +1,774 @@
+// HBM-bound glue kernels (sm_100a): weight packing, layout conversion, BatchNorm statistics + affine fused with
+// LeakyReLU/ReLU (forward and backward), fused GAN-BCE / reconstruction-MSE / feature-matching losses, Adam.
+// All activations are NHWC bf16 viewed as a [P, C] matrix (P = B*H*W); reductions are fp32 with a double-precision
+// combine; 16-byte vector loads, warp-shuffle / shared-memory block reductions.
+// Reference ops replaced: nn.BatchNorm2d + LeakyReLU/ReLU (model.py:12-33,84-140), nn.BCELoss / nn.MSELoss /
+// get_fm_loss (image_translation.py:136-168,267-269,349-350), optim.Adam (image_translation.py:275-287).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void dg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: W[Cs][Cb][16] fp32 -> Wd[Cs][16][Cb] bf16 (cb fastest), Wu[Cb][16][Cs] bf16 (cs fastest)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_wd_kernel(const float* __restrict__ w, bf16* __restrict__ wd, int Cs, int Cb) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Cs * Cb) return;
+  const int cb = (int)(idx % Cb);
+  const int cs = (int)(idx / Cb);
+  const float4* src = reinterpret_cast<const float4*>(w + idx * 16);
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 t = src[i];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+#pragma unroll
+  for (int t = 0; t < 16; ++t) wd[((size_t)cs * 16 + t) * Cb + cb] = __float2bfloat16(v[t]);
+}
+__global__ void pack_wu_kernel(const float* __restrict__ w, bf16* __restrict__ wu, int Cs, int Cb) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Cs * Cb) return;
+  const int cs = (int)(idx % Cs);
+  const int cb = (int)(idx / Cs);
+  const float4* src = reinterpret_cast<const float4*>(w + ((size_t)cs * Cb + cb) * 16);
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 t = src[i];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+#pragma unroll
+  for (int t = 0; t < 16; ++t) wu[((size_t)cb * 16 + t) * Cs + cs] = __float2bfloat16(v[t]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout: NHWC bf16 [B][HW][C] <-> NCHW fp32 [B][C][HW], 32x32 smem tiles
+// ------------------------------------------------------------------------------------------------
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, float* __restrict__ y, int HW, int C) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) tile[i][threadIdx.x] = __bfloat162float(x[((size_t)b * HW + p) * C + c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (p < HW && c < C) y[((size_t)b * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int HW, int C) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (p < HW && c < C) tile[i][threadIdx.x] = x[((size_t)b * C + c) * HW + p];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) y[((size_t)b * HW + p) * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm over [P][C]
+// Block = 256 threads as (cw channel-vectors) x (256/cw rows); VEC = 8 (16-byte loads) or 1 (any C).
+// ------------------------------------------------------------------------------------------------
+struct BnGeom {
+  int cw;          // channel vectors per block row (power of two <= 32)
+  int rows_iter;   // 256 / cw
+  int gx;          // blocks along channels
+  int gy;          // row splits
+  int rows_split;  // rows per split (multiple of rows_iter)
+};
+
+BnGeom bn_geom(long long P, int C, int vec, int sms) {
+  BnGeom g;
+  const int cv = (C + vec - 1) / vec;
+  int cw = 1;
+  while (cw < cv && cw < 32) cw <<= 1;
+  g.cw = cw;
+  g.rows_iter = 256 / cw;
+  g.gx = (cv + cw - 1) / cw;
+  long long want = (4LL * sms + g.gx - 1) / g.gx;
+  long long max_splits = (P + g.rows_iter * 4 - 1) / (g.rows_iter * 4);
+  if (want > max_splits) want = max_splits;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  long long rs = (P + want - 1) / want;
+  rs = (rs + g.rows_iter - 1) / g.rows_iter * g.rows_iter;
+  g.rows_split = (int)rs;
+  g.gy = (int)((P + rs - 1) / rs);
+  return g;
+}
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const bf16* p, float* f) {
+  if (VEC == 8) {
+    bf16x8 v = *reinterpret_cast<const bf16x8*>(p);
+    unpack8(v, f);
+  } else {
+    f[0] = __bfloat162float(*p);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store_vec(bf16* p, const float* f) {
+  if (VEC == 8) {
+    *reinterpret_cast<bf16x8*>(p) = pack8(f);
+  } else {
+    *p = __float2bfloat16(f[0]);
+  }
+}
+
+// Block reduction of VEC*2 per-thread values over the row dimension; result written to part{1,2}[split][C].
+template <int VEC>
+__device__ __forceinline__ void bn_block_reduce_store(float* s1, float* s2, int cw, int rows_iter, int tx, int ty,
+                                                      int c, int C, float* part1, float* part2, int split) {
+  __shared__ float sh1[256 * VEC];
+  __shared__ float sh2[256 * VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    sh1[(ty * cw + tx) * VEC + i] = s1[i];
+    sh2[(ty * cw + tx) * VEC + i] = s2[i];
+  }
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float a = 0.f, b = 0.f;
+      for (int r = 0; r < rows_iter; ++r) {
+        a += sh1[(r * cw + tx) * VEC + i];
+        b += sh2[(r * cw + tx) * VEC + i];
+      }
+      if (c + i < C) {
+        part1[(size_t)split * C + c + i] = a;
+        part2[(size_t)split * C + c + i] = b;
+      }
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bn_stats_partial_kernel(const bf16* __restrict__ z, long long P, int C, int cw, int rows_iter, int rows_split,
+                        float* __restrict__ part_sum, float* __restrict__ part_sq) {
+  const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
+  const int c = (blockIdx.x * cw + tx) * VEC;
+  float s1[VEC], s2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s1[i] = s2[i] = 0.f;
+  if (c < C) {
+    const long long r0 = (long long)blockIdx.y * rows_split;
+    const long long r1 = min(P, r0 + rows_split);
+    for (long long r = r0 + ty; r < r1; r += rows_iter) {
+      float f[VEC];
+      load_vec<VEC>(z + r * C + c, f);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        s1[i] += f[i];
+        s2[i] += f[i] * f[i];
+      }
+    }
+  }
+  bn_block_reduce_store<VEC>(s1, s2, cw, rows_iter, tx, ty, c, C, part_sum, part_sq, blockIdx.y);
+}
+
+// mean/invstd + scale/shift for the apply kernel + running statistics (momentum update, unbiased variance).
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_sq,
+                                         int splits, long long P, int C, float eps, float momentum,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         float* __restrict__ mean, float* __restrict__ invstd,
+                                         float* __restrict__ scale, float* __restrict__ shift,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < splits; ++i) {
+    s += (double)part_sum[(size_t)i * C + c];
+    q += (double)part_sq[(size_t)i * C + c];
+  }
+  const double m = s / (double)P;
+  double var = q / (double)P - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)m;
+  invstd[c] = is;
+  const float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)m * sc;
+  if (running_mean) {
+    const double unbiased = P > 1 ? var * (double)P / (double)(P - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// eval mode: scale/shift from running statistics
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float eps, int C, float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float is = rsqrtf(running_var[c] + eps);
+  const float sc = gamma[c] * is;
+  scale[c] = sc;
+  shift[c] = beta[c] - running_mean[c] * sc;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const bf16* __restrict__ z, bf16* __restrict__ y, long long P, int C,
+                  const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope) {
+  const int cv = (C + VEC - 1) / VEC;
+  const long long total = P * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * VEC;
+    const long long off = (i / cv) * C + c;
+    float f[VEC];
+    load_vec<VEC>(z + off, f);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) f[k] = act_fwd(f[k] * scale[c + k] + shift[c + k], act, slope);
+    store_vec<VEC>(y + off, f);
+  }
+}
+
+// backward pass 1: per-channel sum(g) and sum(g * xhat), g = (dy [+ dy2] [+ coef*bcast]) * act'(y)
+template <int VEC>
+__device__ __forceinline__ void bn_bwd_load_g(const bf16* dy, const bf16* dy2, const float* bcast, float coef,
+                                              long long bcast_rows, const bf16* y, long long r, int C, int c, int act,
+                                              float slope, float* g) {
+  float fy[VEC];
+  load_vec<VEC>(dy + r * C + c, g);
+  load_vec<VEC>(y + r * C + c, fy);
+  if (dy2) {
+    float t[VEC];
+    load_vec<VEC>(dy2 + r * C + c, t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g[i] += t[i];
+  }
+  if (bcast) {
+    const float* bp = bcast + (r % bcast_rows) * C + c;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g[i] += coef * bp[i];
+  }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) g[i] *= act_grad_from_out(fy[i], act, slope);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const float* __restrict__ bcast,
+                      float coef, long long bcast_rows, const bf16* __restrict__ y, const bf16* __restrict__ z,
+                      const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C, int cw,
+                      int rows_iter, int rows_split, int act, float slope, float* __restrict__ part_g,
+                      float* __restrict__ part_gx) {
+  const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
+  const int c = (blockIdx.x * cw + tx) * VEC;
+  float s1[VEC], s2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s1[i] = s2[i] = 0.f;
+  if (c < C) {
+    float mu[VEC], is[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      mu[i] = mean[c + i];
+      is[i] = invstd[c + i];
+    }
+    const long long r0 = (long long)blockIdx.y * rows_split;
+    const long long r1 = min(P, r0 + rows_split);
+    for (long long r = r0 + ty; r < r1; r += rows_iter) {
+      float g[VEC], fz[VEC];
+      bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, y, r, C, c, act, slope, g);
+      load_vec<VEC>(z + r * C + c, fz);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        s1[i] += g[i];
+        s2[i] += g[i] * (fz[i] - mu[i]) * is[i];
+      }
+    }
+  }
+  bn_block_reduce_store<VEC>(s1, s2, cw, rows_iter, tx, ty, c, C, part_g, part_gx, blockIdx.y);
+}
+
+// dgamma/dbeta (accumulated into the fp32 grads with `beta_acc`) and the three per-channel dx coefficients
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part_g, const float* __restrict__ part_gx, int splits,
+                                       long long P, int C, const float* __restrict__ gamma,
+                                       const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float beta_acc, float* __restrict__ coefs) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sg = 0.0, sgx = 0.0;
+  for (int i = 0; i < splits; ++i) {
+    sg += (double)part_g[(size_t)i * C + c];
+    sgx += (double)part_gx[(size_t)i * C + c];
+  }
+  if (dgamma) {
+    dgamma[c] = (beta_acc != 0.f ? beta_acc * dgamma[c] : 0.f) + (float)sgx;
+    dbeta[c] = (beta_acc != 0.f ? beta_acc * dbeta[c] : 0.f) + (float)sg;
+  }
+  coefs[c] = gamma[c] * invstd[c];
+  coefs[C + c] = (float)(sg / (double)P);
+  coefs[2 * C + c] = (float)(sgx / (double)P);
+}
+
+// backward pass 2: dz = gamma*invstd * (g - mean(g) - xhat * mean(g*xhat))
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const float* __restrict__ bcast, float coef,
+                 long long bcast_rows, const bf16* __restrict__ y, const bf16* __restrict__ z,
+                 const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coefs,
+                 bf16* __restrict__ dz, long long P, int C, int act, float slope) {
+  const int cv = (C + VEC - 1) / VEC;
+  const long long total = P * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * VEC;
+    const long long r = i / cv;
+    float g[VEC], fz[VEC];
+    bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, y, r, C, c, act, slope, g);
+    load_vec<VEC>(z + r * C + c, fz);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float xhat = (fz[k] - mean[c + k]) * invstd[c + k];
+      g[k] = coefs[c + k] * (g[k] - coefs[C + c + k] - xhat * coefs[2 * C + c + k]);
+    }
+    store_vec<VEC>(dz + r * C + c, g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v) {
+  __shared__ float sh[8];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;  // valid in warp 0
+}
+
+// GAN BCE on sigmoid(logit): out[0]=dis_loss=0.5*(BCE(pr,1)+BCE(pf,0)), out[1]=gen_loss=BCE(pf,1); log clamp -100
+// (nn.BCELoss semantics).  Also writes the probabilities.
+__global__ void gan_bce_fwd_kernel(const float* __restrict__ logit_real, const float* __restrict__ logit_fake, int B,
+                                   float* __restrict__ p_real, float* __restrict__ p_fake, float* __restrict__ out) {
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float pr = 1.f / (1.f + expf(-logit_real[i]));
+    const float pf = 1.f / (1.f + expf(-logit_fake[i]));
+    p_real[i] = pr;
+    p_fake[i] = pf;
+    a += -fmaxf(logf(pr), -100.f);
+    b += -fmaxf(logf(1.f - pf), -100.f);
+    c += -fmaxf(logf(pf), -100.f);
+  }
+  a = block_sum_256(a);
+  b = block_sum_256(b);
+  c = block_sum_256(c);
+  if (threadIdx.x == 0) {
+    out[0] = 0.5f * (a + b) / (float)B;
+    out[1] = c / (float)B;
+  }
+}
+// d/dlogit of (g_dis*dis_loss + g_gen*gen_loss) through BCELoss and Sigmoid exactly as autograd composes them:
+// dL/dp = (p - y) / max(p(1-p), 1e-12) / B, then * p(1-p).  (p==0 or 1 in fp32 gives 0, as in the reference.)
+__global__ void gan_bce_bwd_kernel(const float* __restrict__ p_real, const float* __restrict__ p_fake, int B,
+                                   float g_dis, float g_gen, float* __restrict__ dlogit_real,
+                                   float* __restrict__ dlogit_fake) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const float pr = p_real[i], pf = p_fake[i];
+  const float invB = 1.f / (float)B;
+  const float sr = pr * (1.f - pr), sf = pf * (1.f - pf);
+  const float dpr = 0.5f * g_dis * (pr - 1.f) / fmaxf(sr, 1e-12f) * invB;
+  const float dpf = (0.5f * g_dis * (pf - 0.f) + g_gen * (pf - 1.f)) / fmaxf(sf, 1e-12f) * invB;
+  if (dlogit_real) dlogit_real[i] = dpr * sr;
+  if (dlogit_fake) dlogit_fake[i] = dpf * sf;
+}
+
+// sigmoid forward/backward on tiny [B] vectors (module API path: prob output of the Discriminator)
+__global__ void sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = 1.f / (1.f + expf(-x[i]));
+}
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx,
+                                   int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dx[i] = dy[i] * y[i] * (1.f - y[i]);
+}
+
+// MSE: partial sums of (a-b)^2 per block, then finalize to mean
+__global__ void __launch_bounds__(256)
+mse_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ part) {
+  float s = 0.f;
+  const long long n4 = n >> 2;
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 x = a4[i], y = b4[i];
+    const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+    s += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      const float d = a[i] - b[i];
+      s += d * d;
+    }
+  s = block_sum_256(s);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void sum_finalize_kernel(const float* __restrict__ part, int n, double scale, float* __restrict__ out,
+                                    int accumulate) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) s += (double)part[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) {
+    const float v = (float)(s * scale);
+    out[0] = accumulate ? out[0] + v : v;
+  }
+}
+// da (+)= coef * (a - b)
+__global__ void __launch_bounds__(256)
+mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float coef,
+               float* __restrict__ da, int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = coef * (a[i] - b[i]);
+    da[i] = accumulate ? da[i] + v : v;
+  }
+}
+
+// Feature matching on NHWC bf16 feats [B][n] (n = H*W*C): d = mean_b real - mean_b fake (kept fp32 for backward),
+// block partial sums of d^2.
+__global__ void __launch_bounds__(256)
+fm_partial_kernel(const bf16* __restrict__ real, const bf16* __restrict__ fake, int B, long long n,
+                  float* __restrict__ diff, float* __restrict__ part) {
+  float s = 0.f;
+  const long long n8 = n >> 3;
+  const float invB = 1.f / (float)B;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float ar[8], af[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ar[k] = af[k] = 0.f;
+    for (int b = 0; b < B; ++b) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(real + (size_t)b * n + i * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ar[k] += f[k];
+      unpack8(*reinterpret_cast<const bf16x8*>(fake + (size_t)b * n + i * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) af[k] += f[k];
+    }
+    float d[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      d[k] = (ar[k] - af[k]) * invB;
+      s += d[k] * d[k];
+    }
+    if (diff) {
+      *reinterpret_cast<float4*>(diff + i * 8) = make_float4(d[0], d[1], d[2], d[3]);
+      *reinterpret_cast<float4*>(diff + i * 8 + 4) = make_float4(d[4], d[5], d[6], d[7]);
+    }
+  }
+  s = block_sum_256(s);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+// dfeat[b][i] = coef * diff[i]  (bf16, broadcast over batch)
+__global__ void __launch_bounds__(256)
+fm_bwd_kernel(const float* __restrict__ diff, int B, long long n, float coef, bf16* __restrict__ dfeat) {
+  const long long n8 = n >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float d[8];
+    const float4 a = *reinterpret_cast<const float4*>(diff + i * 8);
+    const float4 b4 = *reinterpret_cast<const float4*>(diff + i * 8 + 4);
+    d[0] = coef * a.x; d[1] = coef * a.y; d[2] = coef * a.z; d[3] = coef * a.w;
+    d[4] = coef * b4.x; d[5] = coef * b4.y; d[6] = coef * b4.z; d[7] = coef * b4.w;
+    const bf16x8 v = pack8(d);
+    for (int b = 0; b < B; ++b) *reinterpret_cast<bf16x8*>(dfeat + (size_t)b * n + i * 8) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam (coupled L2 weight decay, torch.optim.Adam op order), flat fp32 buffers
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+            float grad_scale) {
+  const float step_size = lr / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    const float gi = g[i] * grad_scale + wd * pi;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;       // exp_avg.lerp_(grad, 1-beta1)
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+int ew_grid(long long work_items, int sms) {
+  long long blocks = (work_items + 255) / 256;
+  const long long cap = (long long)sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+int g_sms = 0;
+int sms() {
+  if (!g_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dg_last_error(void) { return g_err; }
+int dg_version(void) { return 1; }
+
+// Fails loudly unless the current device is a Blackwell sm_100 part with a loadable kernel image.
+int dg_device_check(void) {
+  int dev = 0, major = 0, minor = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    dg_set_error("no CUDA device: %s", cudaGetErrorString(e));
+    return DG_ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    dg_set_error("discogan_modernized_b200 kernels are built for sm_100a only; device is sm_%d%d", major, minor);
+    return DG_ERR_ARCH;
+  }
+  return DG_OK;
+}
+
+int dg_pack_weights(const float* w, void* wd, void* wu, int Cs, int Cb, cudaStream_t stream) {
+  DG_CHECK_ARG(Cs > 0 && Cb > 0 && w, "pack_weights: bad args");
+  const long long n = (long long)Cs * Cb;
+  if (wd) pack_wd_kernel<<<dg_ceil_div(n, 256), 256, 0, stream>>>(w, (bf16*)wd, Cs, Cb);
+  if (wu) pack_wu_kernel<<<dg_ceil_div(n, 256), 256, 0, stream>>>(w, (bf16*)wu, Cs, Cb);
+  DG_CHECK_LAUNCH("pack_weights");
+  return DG_OK;
+}
+
+int dg_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, cudaStream_t stream) {
+  DG_CHECK_ARG(B > 0 && HW > 0 && C > 0 && B <= 65535, "nhwc_to_nchw: bad dims");
+  dim3 grid(dg_ceil_div(HW, 32), dg_ceil_div(C, 32), B), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, stream>>>((const bf16*)x, y, HW, C);
+  DG_CHECK_LAUNCH("nhwc_to_nchw");
+  return DG_OK;
+}
+int dg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int HW, int C, cudaStream_t stream) {
+  DG_CHECK_ARG(B > 0 && HW > 0 && C > 0 && B <= 65535, "nchw_to_nhwc: bad dims");
+  dim3 grid(dg_ceil_div(HW, 32), dg_ceil_div(C, 32), B), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, stream>>>(x, (bf16*)y, HW, C);
+  DG_CHECK_LAUNCH("nchw_to_nhwc");
+  return DG_OK;
+}
+
+// scratch layout for BN calls: floats [2 * splits_max * C]; query with dg_bn_scratch_floats
+size_t dg_bn_scratch_floats(long long P, int C) {
+  const int vec = (C % 8 == 0) ? 8 : 1;
+  BnGeom g = bn_geom(P, C, vec, sms());
+  return (size_t)2 * g.gy * C;
+}
+
+// Training-mode statistics of z[P][C]: mean, invstd, apply coefficients (scale, shift) and the running-stat update
+// (running_* may be NULL).  stats = float[4*C] = {mean, invstd, scale, shift}.
+int dg_bn_stats(const void* z, long long P, int C, const float* gamma, const float* beta, float eps, float momentum,
+                float* stats, float* running_mean, float* running_var, float* scratch, cudaStream_t stream) {
+  DG_CHECK_ARG(P > 0 && C > 0 && z && stats && scratch, "bn_stats: bad args");
+  const int vec = (C % 8 == 0) ? 8 : 1;
+  BnGeom g = bn_geom(P, C, vec, sms());
+  float* ps = scratch;
+  float* pq = scratch + (size_t)g.gy * C;
+  dim3 grid(g.gx, g.gy);
+  if (vec == 8)
+    bn_stats_partial_kernel<8><<<grid, 256, 0, stream>>>((const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq);
+  else
+    bn_stats_partial_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq);
+  DG_CHECK_LAUNCH("bn_stats_partial");
+  bn_stats_finalize_kernel<<<dg_ceil_div(C, 128), 128, 0, stream>>>(ps, pq, g.gy, P, C, eps, momentum, gamma, beta,
+                                                                    stats, stats + C, stats + 2 * C, stats + 3 * C,
+                                                                    running_mean, running_var);
+  DG_CHECK_LAUNCH("bn_stats_finalize");
+  return DG_OK;
+}
+
+int dg_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, int C, float* stats, cudaStream_t stream) {
+  DG_CHECK_ARG(C > 0 && stats, "bn_eval_coeffs: bad args");
+  bn_eval_coeffs_kernel<<<dg_ceil_div(C, 128), 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, C,
+                                                                 stats + 2 * C, stats + 3 * C);
+  DG_CHECK_LAUNCH("bn_eval_coeffs");
+  return DG_OK;
+}
+
+// y = act(z * scale + shift)
+int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats, int act, float slope,
+                  cudaStream_t stream) {
+  DG_CHECK_ARG(P > 0 && C > 0 && z && y && stats, "bn_act_fwd: bad args");
+  if (C % 8 == 0)
+    bn_act_fwd_kernel<8><<<ew_grid(P * (C / 8), sms()), 256, 0, stream>>>((const bf16*)z, (bf16*)y, P, C, stats + 2 * C,
+                                                                         stats + 3 * C, act, slope);
+  else
+    bn_act_fwd_kernel<1><<<ew_grid(P * C, sms()), 256, 0, stream>>>((const bf16*)z, (bf16*)y, P, C, stats + 2 * C,
+                                                                   stats + 3 * C, act, slope);
+  DG_CHECK_LAUNCH("bn_act_fwd");
+  return DG_OK;
+}
+
+// Backward of y = act(BN_train(z)).  Upstream gradient g = dy (+ dy2) (+ bcast_coef * bcast[row % bcast_rows]).
+// dgamma/dbeta: fp32 grads, new = grad_beta*old + value (grad_beta 0 overwrites).  coefs: float[3*C] scratch.
+int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bcast_coef, long long bcast_rows,
+                  const void* y, const void* z, const float* stats, const float* gamma, long long P, int C, int act,
+                  float slope, float* dgamma, float* dbeta, float grad_beta, void* dz, float* coefs, float* scratch,
+                  cudaStream_t stream) {
+  DG_CHECK_ARG(P > 0 && C > 0 && dy && y && z && stats && dz && coefs && scratch, "bn_act_bwd: bad args");
+  DG_CHECK_ARG(!bcast || bcast_rows > 0, "bn_act_bwd: bcast_rows must be positive");
+  const int vec = (C % 8 == 0) ? 8 : 1;
+  BnGeom g = bn_geom(P, C, vec, sms());
+  float* pg = scratch;
+  float* pgx = scratch + (size_t)g.gy * C;
+  dim3 grid(g.gx, g.gy);
+  const float* mean = stats;
+  const float* invstd = stats + C;
+  if (vec == 8)
+    bn_bwd_partial_kernel<8><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
+                                                       (const bf16*)y, (const bf16*)z, mean, invstd, P, C, g.cw,
+                                                       g.rows_iter, g.rows_split, act, slope, pg, pgx);
+  else
+    bn_bwd_partial_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
+                                                       (const bf16*)y, (const bf16*)z, mean, invstd, P, C, g.cw,
+                                                       g.rows_iter, g.rows_split, act, slope, pg, pgx);
+  DG_CHECK_LAUNCH("bn_bwd_partial");
+  bn_bwd_finalize_kernel<<<dg_ceil_div(C, 128), 128, 0, stream>>>(pg, pgx, g.gy, P, C, gamma, invstd, dgamma, dbeta,
+                                                                  grad_beta, coefs);
+  DG_CHECK_LAUNCH("bn_bwd_finalize");
+  if (vec == 8)
+    bn_bwd_dx_kernel<8><<<ew_grid(P * (C / 8), sms()), 256, 0, stream>>>(
+        (const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows, (const bf16*)y, (const bf16*)z, mean, invstd,
+        coefs, (bf16*)dz, P, C, act, slope);
+  else
+    bn_bwd_dx_kernel<1><<<ew_grid(P * C, sms()), 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef,
+                                                                  bcast_rows, (const bf16*)y, (const bf16*)z, mean,
+                                                                  invstd, coefs, (bf16*)dz, P, C, act, slope);
+  DG_CHECK_LAUNCH("bn_bwd_dx");
+  return DG_OK;
+}
+
+int dg_gan_bce_fwd(const float* logit_real, const float* logit_fake, int B, float* p_real, float* p_fake, float* out2,
+                   cudaStream_t stream) {
+  DG_CHECK_ARG(B > 0 && logit_real && logit_fake && p_real && p_fake && out2, "gan_bce_fwd: bad args");
+  gan_bce_fwd_kernel<<<1, 256, 0, stream>>>(logit_real, logit_fake, B, p_real, p_fake, out2);
+  DG_CHECK_LAUNCH("gan_bce_fwd");
+  return DG_OK;
+}
+int dg_gan_bce_bwd(const float* p_real, const float* p_fake, int B, float g_dis, float g_gen, float* dlogit_real,
+                   float* dlogit_fake, cudaStream_t stream) {
+  DG_CHECK_ARG(B > 0 && p_real && p_fake, "gan_bce_bwd: bad args");
+  gan_bce_bwd_kernel<<<dg_ceil_div(B, 128), 128, 0, stream>>>(p_real, p_fake, B, g_dis, g_gen, dlogit_real,
+                                                              dlogit_fake);
+  DG_CHECK_LAUNCH("gan_bce_bwd");
+  return DG_OK;
+}
+int dg_sigmoid_fwd(const float* x, float* y, int n, cudaStream_t stream) {
+  DG_CHECK_ARG(n > 0, "sigmoid_fwd: bad args");
+  sigmoid_fwd_kernel<<<dg_ceil_div(n, 128), 128, 0, stream>>>(x, y, n);
+  DG_CHECK_LAUNCH("sigmoid_fwd");
+  return DG_OK;
+}
+int dg_sigmoid_bwd(const float* y, const float* dy, float* dx, int n, cudaStream_t stream) {
+  DG_CHECK_ARG(n > 0, "sigmoid_bwd: bad args");
+  sigmoid_bwd_kernel<<<dg_ceil_div(n, 128), 128, 0, stream>>>(y, dy, dx, n);
+  DG_CHECK_LAUNCH("sigmoid_bwd");
+  return DG_OK;
+}
+
+// out[0] = mean((a-b)^2); scratch: float[dg_reduce_scratch_floats()]
+size_t dg_reduce_scratch_floats(void) { return (size_t)sms() * 8; }
+
+int dg_mse_fwd(const float* a, const float* b, long long n, float* out, float* scratch, cudaStream_t stream) {
+  DG_CHECK_ARG(n > 0 && a && b && out && scratch, "mse_fwd: bad args");
+  DG_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0, "mse_fwd: inputs must be 16-byte aligned");
+  const int grid = ew_grid(n / 4 + 1, sms());
+  mse_partial_kernel<<<grid, 256, 0, stream>>>(a, b, n, scratch);
+  DG_CHECK_LAUNCH("mse_partial");
+  sum_finalize_kernel<<<1, 32, 0, stream>>>(scratch, grid, 1.0 / (double)n, out, 0);
+  DG_CHECK_LAUNCH("mse_finalize");
+  return DG_OK;
+}
+// da (+)= g * 2/n * (a-b)
+int dg_mse_bwd(const float* a, const float* b, long long n, float g, float* da, int accumulate, cudaStream_t stream) {
+  DG_CHECK_ARG(n > 0 && a && b && da, "mse_bwd: bad args");
+  mse_bwd_kernel<<<ew_grid(n, sms()), 256, 0, stream>>>(a, b, n, g * 2.f / (float)n, da, accumulate);
+  DG_CHECK_LAUNCH("mse_bwd");
+  return DG_OK;
+}
+
+// out[0] (+)= mean_i (mean_b real - mean_b fake)^2 over n = H*W*C; diff (fp32 [n]) optional, kept for the backward.
+int dg_fm_fwd(const void* real, const void* fake, int B, long long n, float* diff, float* out, int accumulate,
+              float* scratch, cudaStream_t stream) {
+  DG_CHECK_ARG(B > 0 && n > 0 && n % 8 == 0 && real && fake && out && scratch, "fm_fwd: bad args (n must be a multiple of 8)");
+  const int grid = ew_grid(n / 8, sms());
+  fm_partial_kernel<<<grid, 256, 0, stream>>>((const bf16*)real, (const bf16*)fake, B, n, diff, scratch);
+  DG_CHECK_LAUNCH("fm_partial");
+  sum_finalize_kernel<<<1, 32, 0, stream>>>(scratch, grid, 1.0 / (double)n, out, accumulate);
+  DG_CHECK_LAUNCH("fm_finalize");
+  return DG_OK;
+}
+// dfeat_fake[b][i] = -g * 2/(n*B) * diff[i]   (use +g for the real branch)
+int dg_fm_bwd(const float* diff, int B, long long n, float g, void* dfeat, cudaStream_t stream) {
+  DG_CHECK_ARG(B > 0 && n > 0 && n % 8 == 0 && diff && dfeat, "fm_bwd: bad args");
+  fm_bwd_kernel<<<ew_grid(n / 8, sms()), 256, 0, stream>>>(diff, B, n, -g * 2.f / ((float)n * (float)B), (bf16*)dfeat);
+  DG_CHECK_LAUNCH("fm_bwd");
+  return DG_OK;
+}
+
+// One Adam step over flat fp32 buffers; `step` is the 1-based step count of this parameter group.
+int dg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream) {
+  DG_CHECK_ARG(n > 0 && p && g && m && v && step >= 1, "adam_step: bad args");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<ew_grid(n, sms()), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                     (float)sqrt(bc2), grad_scale);
+  DG_CHECK_LAUNCH("adam_step");
+  return DG_OK;
+}
+
+}  // extern "C"

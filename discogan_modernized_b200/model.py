@@ -1,0 +1,398 @@
+"""Generator / Discriminator with the reference's nn.Module API, running on the sm_100a kernels.
+
+Drop-in boundary (reference ``model.py``): same class names, constructor arguments, forward
+outputs, ``state_dict`` keys/shapes and parameter order -- ``Discriminator`` mirrors
+``model.py:5-69`` and ``Generator`` ``model.py:72-225`` -- so the reference entry points
+(``image_translation.py:260-263``, ``inference.py:126-136``) can import these instead.  The
+``torch.nn`` layer objects below are parameter containers only (they give the reference's default
+initialisation and state-dict layout); the arithmetic is done by the hand-written kernels through
+one ``torch.autograd.Function`` per network.  Internally activations are NHWC bf16 with fp32
+accumulation and fp32 BatchNorm statistics.  There is no CPU or cuDNN path: a non-CUDA input raises.
+
+``image_size`` (default 512, the only size the reference supports -- SURVEY.md F1) selects a member
+of the depth-parametrised family: ``n_down = log2(S) - 2`` stride-2 layers with channels
+``64 * 2**min(i, 5)``.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import ACT_LRELU, ACT_RELU
+
+LRELU_SLOPE = 0.2
+
+
+def family_channels(image_size: int):
+    n_down = int(round(math.log2(image_size))) - 2
+    if image_size < 16 or 2 ** (n_down + 2) != image_size:
+        raise ValueError(f"image_size must be a power of two >= 16, got {image_size}")
+    return [64 * 2 ** min(i, 5) for i in range(n_down)]
+
+
+# ---------------------------------------------------------------------------------------------
+# packed bf16 weights, refreshed when the fp32 parameter changes
+# ---------------------------------------------------------------------------------------------
+class _PackedWeights:
+    """bf16 GEMM-layout copies of the fp32 conv weights, keyed by parameter; re-packed when the
+    parameter's version counter or storage changes.  Code that rewrites parameters behind autograd's
+    back (the fused Adam kernel) calls ``invalidate()``."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, p, want_wd, want_wu):
+        key = id(p)
+        tag = (p._version, p.data_ptr())
+        ent = self._cache.get(key)
+        if ent is None or ent[0] != tag:
+            wd, wu = ops.pack_weights(p.detach(), want_wd, want_wu)
+            ent = (tag, wd, wu)
+            self._cache[key] = ent
+        return ent[1], ent[2]
+
+    def invalidate(self):
+        self._cache.clear()
+
+
+def _new_packed():
+    return _PackedWeights()
+
+
+def _grad_buf(p):
+    """fp32 gradient buffer of a parameter (allocated zeroed on first use, then accumulated into)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+def _check_input(x, image_size, training):
+    if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != image_size or x.shape[3] != image_size:
+        raise RuntimeError(f"expected input of shape [B, 3, {image_size}, {image_size}], got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("discogan_modernized_b200 runs on CUDA (sm_100a) only; move the module and input to the GPU")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"expected a float32 image, got {x.dtype}")
+    if training and x.shape[0] < 2:
+        raise ValueError("Expected more than 1 value per channel when training (BatchNorm over a 1x1 map needs B >= 2)")
+
+
+class _BnSave:
+    __slots__ = ("z", "y", "stats")
+
+    def __init__(self, z, y, stats):
+        self.z, self.y, self.stats = z, y, stats
+
+
+def _bn_act(z, bn, act, training):
+    """z: NHWC bf16 (any leading dims, channels last).  Returns (y, stats)."""
+    C = z.shape[-1]
+    z2 = z.view(-1, C)
+    if training or not bn.track_running_stats:
+        if z2.shape[0] < 2:
+            raise ValueError("Expected more than 1 value per channel when training")
+        rm, rv = (bn.running_mean, bn.running_var) if (training and bn.track_running_stats) else (None, None)
+        stats = ops.bn_stats(z2, bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps,
+                             bn.momentum if bn.momentum is not None else 0.1)
+        if rm is not None:
+            bn.num_batches_tracked.add_(1)
+    else:
+        stats = ops.bn_eval_stats(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
+    y = ops.bn_act_fwd(z2, stats, act, LRELU_SLOPE).view(z.shape)
+    return y, stats
+
+
+def _bn_act_bwd(dy, sv, bn, act, need_wgrad, dy2=None, bcast=None, bcast_coef=0.0):
+    C = sv.z.shape[-1]
+    dgamma = _grad_buf(bn.weight) if need_wgrad else None
+    dbeta = _grad_buf(bn.bias) if need_wgrad else None
+    dz = ops.bn_act_bwd(dy.view(-1, C), sv.y.view(-1, C), sv.z.view(-1, C), sv.stats, bn.weight.detach(), act,
+                        LRELU_SLOPE, dgamma, dbeta, 1.0, None if dy2 is None else dy2.view(-1, C), bcast, bcast_coef)
+    return dz.view(sv.z.shape)
+
+
+# ---------------------------------------------------------------------------------------------
+# Discriminator
+# ---------------------------------------------------------------------------------------------
+class _DiscCtx:
+    __slots__ = ("x", "y1", "bn", "B")
+
+
+def discriminator_forward(mod, x, save=True):
+    """-> (logit fp32 [B], feats: list of NHWC bf16 tensors, ctx)."""
+    training = mod.training
+    _check_input(x, mod.image_size, training)
+    x = x.contiguous()
+    pk = mod._packed
+    y = ops.conv_c3_in_fwd(x, mod.conv1.weight.detach(), LRELU_SLOPE)
+    ctx = _DiscCtx()
+    ctx.x, ctx.y1, ctx.bn, ctx.B = (x if save else None), y, [], x.shape[0]
+    feats = []
+    for k in range(2, mod.n_down + 1):
+        conv, bn = getattr(mod, f"conv{k}"), getattr(mod, f"bn{k}")
+        wd, _ = pk.get(conv.weight, True, True)
+        z = ops.conv_down(y, wd)
+        y, stats = _bn_act(z, bn, ACT_LRELU, training)
+        ctx.bn.append(_BnSave(z if save else None, y, stats))
+        feats.append(y)
+    head = getattr(mod, f"conv{mod.n_down + 1}")
+    wd, _ = pk.get(head.weight, True, False)
+    logit = ops.fc_down(y.view(x.shape[0], -1), wd.view(1, -1), out_f32=True).view(-1)
+    return logit, feats, ctx
+
+
+def discriminator_backward(mod, ctx, dlogit, dfeats=None, fm_bcast=None, need_dx=True, need_wgrad=True,
+                           dx_out=None, dx_accumulate=False):
+    """dlogit fp32 [B]; dfeats[i] optional bf16 NHWC grads on feats; fm_bcast[i] optional (diff, coef).
+    Returns d(loss)/d(input image) (fp32 NCHW) or None."""
+    pk = mod._packed
+    B = ctx.B
+    head = getattr(mod, f"conv{mod.n_down + 1}")
+    wd, _ = pk.get(head.weight, True, False)
+    y_last = ctx.bn[-1].y
+    dl = dlogit.contiguous().view(B, 1)
+    if need_wgrad:
+        ops.fc_wgrad(dl, y_last.view(B, -1), _grad_buf(head.weight), 1.0)
+    dy = ops.fc_up(dl, wd.view(1, -1)).view(y_last.shape)
+    for k in range(mod.n_down, 1, -1):
+        i = k - 2
+        conv, bn = getattr(mod, f"conv{k}"), getattr(mod, f"bn{k}")
+        sv = ctx.bn[i]
+        dy2 = dfeats[i] if dfeats is not None else None
+        bc, coef = fm_bcast[i] if (fm_bcast is not None and fm_bcast[i] is not None) else (None, 0.0)
+        dz = _bn_act_bwd(dy, sv, bn, ACT_LRELU, need_wgrad, dy2, bc, coef)
+        y_prev = ctx.bn[i - 1].y if i > 0 else ctx.y1
+        if need_wgrad:
+            ops.conv_wgrad(dz, y_prev, _grad_buf(conv.weight), 1.0)
+        _, wu = pk.get(conv.weight, True, True)
+        dy = ops.conv_up(dz, wu)
+    dx = None
+    if need_dx:
+        dx = dx_out if dx_out is not None else torch.empty_like(ctx.x)
+    if need_dx or need_wgrad:
+        ops.conv_c3_in_bwd(ctx.x, mod.conv1.weight.detach(), ctx.y1, dy, dx, dx_accumulate and dx_out is not None,
+                           _grad_buf(mod.conv1.weight) if need_wgrad else None, LRELU_SLOPE)
+    return dx
+
+
+class _DiscFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        logit, feats, sv = discriminator_forward(mod, x, save=True)
+        prob = ops.sigmoid_fwd(logit)
+        ctx.mod, ctx.sv, ctx.prob = mod, sv, prob
+        ctx.feat_dtype = mod.feature_dtype
+        if mod.feature_dtype == torch.bfloat16:
+            outs = [f.permute(0, 3, 1, 2) for f in feats]
+        else:
+            outs = [ops.nhwc_to_nchw_f32(f) for f in feats]
+        return (prob.view(-1, 1, 1, 1),) + tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dprob, *dfeats):
+        mod, sv = ctx.mod, ctx.sv
+        if not mod.training:
+            raise RuntimeError("backward through eval-mode BatchNorm is not supported by the B200 kernels")
+        B = sv.B
+        if dprob is None:
+            dlogit = torch.zeros(B, dtype=torch.float32, device=ctx.prob.device)
+        else:
+            dlogit = ops.sigmoid_bwd(ctx.prob, dprob.reshape(-1).float().contiguous())
+        dfs = []
+        for g in dfeats:
+            if g is None:
+                dfs.append(None)
+            elif g.dtype == torch.bfloat16:
+                dfs.append(g.permute(0, 2, 3, 1).contiguous())
+            else:
+                dfs.append(ops.nchw_f32_to_nhwc(g.float().contiguous()))
+        need_dx = ctx.needs_input_grad[1]
+        need_wgrad = any(ctx.needs_input_grad[2:])
+        dx = discriminator_backward(mod, sv, dlogit, dfs, None, need_dx, need_wgrad)
+        return (None, dx) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+class Discriminator(nn.Module):
+    """Reference ``model.py:5-69``.  forward(x[B,3,S,S]) -> (prob[B,1,1,1], [feat_2 .. feat_n_down])."""
+
+    def __init__(self, image_size: int = 512):
+        super().__init__()
+        ch = family_channels(image_size)
+        self.image_size = image_size
+        self.n_down = len(ch)
+        self.conv1 = nn.Conv2d(3, ch[0], 4, 2, 1, bias=False)
+        self.relu1 = nn.LeakyReLU(LRELU_SLOPE, inplace=True)
+        for i in range(1, self.n_down):
+            k = i + 1
+            setattr(self, f"conv{k}", nn.Conv2d(ch[i - 1], ch[i], 4, 2, 1, bias=False))
+            setattr(self, f"bn{k}", nn.BatchNorm2d(ch[i]))
+            setattr(self, f"relu{k}", nn.LeakyReLU(LRELU_SLOPE, inplace=True))
+        setattr(self, f"conv{self.n_down + 1}", nn.Conv2d(ch[-1], 1, 4, 1, 0, bias=False))
+        self.sigmoid = nn.Sigmoid()
+        self.feature_dtype = torch.float32  # torch.bfloat16: zero-copy NHWC-strided views (used by the fused step)
+        self._packed = _new_packed()
+
+    def forward(self, input_tensor):
+        if torch.is_grad_enabled() and (input_tensor.requires_grad or any(p.requires_grad for p in self.parameters())):
+            out = _DiscFn.apply(self, input_tensor, *list(self.parameters()))
+            return out[0], list(out[1:])
+        logit, feats, _ = discriminator_forward(self, input_tensor, save=False)
+        prob = ops.sigmoid_fwd(logit).view(-1, 1, 1, 1)
+        if self.feature_dtype == torch.bfloat16:
+            return prob, [f.permute(0, 3, 1, 2) for f in feats]
+        return prob, [ops.nhwc_to_nchw_f32(f) for f in feats]
+
+
+# ---------------------------------------------------------------------------------------------
+# Generator
+# ---------------------------------------------------------------------------------------------
+class _GenCtx:
+    __slots__ = ("x", "y1", "enc", "head", "dec0", "dec", "out", "B")
+
+
+def _gen_layers(mod):
+    """Index helpers into the reference's Sequential numbering (model.py:79-143)."""
+    n = mod.n_down
+    enc_convs = [mod.encoder[0]] + [mod.encoder[2 + 3 * (i - 1)] for i in range(1, n)]
+    enc_bns = [None] + [mod.encoder[3 + 3 * (i - 1)] for i in range(1, n)]
+    head_conv, head_bn = mod.encoder[2 + 3 * (n - 1)], mod.encoder[3 + 3 * (n - 1)]
+    dec_convs = [mod.decoder[3 * j] for j in range(n + 1)]
+    dec_bns = [mod.decoder[3 * j + 1] for j in range(n)]
+    return enc_convs, enc_bns, head_conv, head_bn, dec_convs, dec_bns
+
+
+def generator_forward(mod, x, save=True):
+    """-> (image fp32 NCHW [B,3,S,S] in (0,1), ctx)."""
+    training = mod.training
+    _check_input(x, mod.image_size, training)
+    x = x.contiguous()
+    B = x.shape[0]
+    pk = mod._packed
+    enc_convs, enc_bns, head_conv, head_bn, dec_convs, dec_bns = _gen_layers(mod)
+    ctx = _GenCtx()
+    ctx.B, ctx.x = B, (x if save else None)
+    y = ops.conv_c3_in_fwd(x, enc_convs[0].weight.detach(), LRELU_SLOPE)
+    ctx.y1, ctx.enc = y, []
+    for conv, bn in zip(enc_convs[1:], enc_bns[1:]):
+        wd, _ = pk.get(conv.weight, True, True)
+        z = ops.conv_down(y, wd)
+        y, stats = _bn_act(z, bn, ACT_LRELU, training)
+        ctx.enc.append(_BnSave(z if save else None, y, stats))
+    # 4x4 valid conv to the 100-d bottleneck (model.py:107-109)
+    wd, _ = pk.get(head_conv.weight, True, False)
+    z = ops.fc_down(y.view(B, -1), wd.view(wd.shape[0], -1))
+    y, stats = _bn_act(z, head_bn, ACT_LRELU, training)
+    ctx.head = _BnSave(z if save else None, y, stats)
+    # ConvTranspose2d(100, C, 4, 1, 0) from the 1x1 bottleneck (model.py:114-116)
+    wd0, _ = pk.get(dec_convs[0].weight, True, False)
+    C = wd0.shape[2]
+    z = ops.fc_up(y, wd0.view(wd0.shape[0], -1)).view(B, 4, 4, C)
+    y, stats = _bn_act(z, dec_bns[0], ACT_RELU, training)
+    ctx.dec0 = _BnSave(z if save else None, y, stats)
+    ctx.dec = []
+    for conv, bn in zip(dec_convs[1:-1], dec_bns[1:]):
+        _, wu = pk.get(conv.weight, True, True)
+        z = ops.conv_up(y, wu)
+        y, stats = _bn_act(z, bn, ACT_RELU, training)
+        ctx.dec.append(_BnSave(z if save else None, y, stats))
+    out = ops.convT_c3_out_fwd(y, dec_convs[-1].weight.detach())
+    ctx.out = out
+    return out, ctx
+
+
+def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=None, dx_accumulate=False):
+    """dout: d(loss)/d(output image), fp32 NCHW.  Returns d(loss)/d(input image) or None."""
+    pk = mod._packed
+    B = ctx.B
+    enc_convs, enc_bns, head_conv, head_bn, dec_convs, dec_bns = _gen_layers(mod)
+    dec_in = [ctx.dec0] + ctx.dec          # dec_in[j].y is the input of dec_convs[j+1]
+    last = dec_convs[-1]
+    dy = ops.convT_c3_out_bwd(dec_in[-1].y, last.weight.detach(), ctx.out, dout.contiguous(), True,
+                              _grad_buf(last.weight) if need_wgrad else None)
+    for j in range(len(ctx.dec), 0, -1):
+        conv, bn = dec_convs[j], dec_bns[j]
+        sv = ctx.dec[j - 1]
+        dz = _bn_act_bwd(dy, sv, bn, ACT_RELU, need_wgrad)
+        x_in = dec_in[j - 1].y
+        if need_wgrad:
+            ops.conv_wgrad(x_in, dz, _grad_buf(conv.weight), 1.0)      # convT wgrad: small = input, big = dz
+        wd, _ = pk.get(conv.weight, True, True)
+        dy = ops.conv_down(dz, wd)                                      # convT dgrad
+    # decoder.0: ConvTranspose2d(100, C, 4, 1, 0)
+    dz = _bn_act_bwd(dy, ctx.dec0, dec_bns[0], ACT_RELU, need_wgrad)
+    wd0, _ = pk.get(dec_convs[0].weight, True, False)
+    if need_wgrad:
+        ops.fc_wgrad(ctx.head.y, dz.view(B, -1), _grad_buf(dec_convs[0].weight), 1.0)
+    dy = ops.fc_down(dz.view(B, -1), wd0.view(wd0.shape[0], -1))
+    # encoder head: Conv2d(C, 100, 4, 1, 0)
+    dz = _bn_act_bwd(dy, ctx.head, head_bn, ACT_LRELU, need_wgrad)
+    y_last = ctx.enc[-1].y
+    if need_wgrad:
+        ops.fc_wgrad(dz, y_last.view(B, -1), _grad_buf(head_conv.weight), 1.0)
+    wdh, _ = pk.get(head_conv.weight, True, False)
+    dy = ops.fc_up(dz, wdh.view(wdh.shape[0], -1)).view(y_last.shape)
+    for i in range(len(ctx.enc), 0, -1):
+        conv, bn = enc_convs[i], enc_bns[i]
+        sv = ctx.enc[i - 1]
+        dz = _bn_act_bwd(dy, sv, bn, ACT_LRELU, need_wgrad)
+        y_prev = ctx.enc[i - 2].y if i > 1 else ctx.y1
+        if need_wgrad:
+            ops.conv_wgrad(dz, y_prev, _grad_buf(conv.weight), 1.0)
+        _, wu = pk.get(conv.weight, True, True)
+        dy = ops.conv_up(dz, wu)
+    dx = None
+    if need_dx:
+        dx = dx_out if dx_out is not None else torch.empty_like(ctx.x)
+    if need_dx or need_wgrad:
+        ops.conv_c3_in_bwd(ctx.x, enc_convs[0].weight.detach(), ctx.y1, dy, dx, dx_accumulate and dx_out is not None,
+                           _grad_buf(enc_convs[0].weight) if need_wgrad else None, LRELU_SLOPE)
+    return dx
+
+
+class _GenFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        out, sv = generator_forward(mod, x, save=True)
+        ctx.mod, ctx.sv = mod, sv
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        mod = ctx.mod
+        if not mod.training:
+            raise RuntimeError("backward through eval-mode BatchNorm is not supported by the B200 kernels")
+        need_dx = ctx.needs_input_grad[1]
+        need_wgrad = any(ctx.needs_input_grad[2:])
+        dx = generator_backward(mod, ctx.sv, dout.float(), need_dx, need_wgrad)
+        return (None, dx) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+class Generator(nn.Module):
+    """Reference ``model.py:72-225``: forward(x[B,3,S,S]) -> image [B,3,S,S].  ``extra_layers`` is accepted and
+    has no effect, exactly as in the reference (both branches build the same layers)."""
+
+    def __init__(self, extra_layers: bool = False, image_size: int = 512):
+        super().__init__()
+        ch = family_channels(image_size)
+        self.image_size = image_size
+        self.n_down = len(ch)
+        self.main = None
+        enc = [nn.Conv2d(3, ch[0], 4, 2, 1, bias=False), nn.LeakyReLU(LRELU_SLOPE, inplace=True)]
+        for i in range(1, len(ch)):
+            enc += [nn.Conv2d(ch[i - 1], ch[i], 4, 2, 1, bias=False), nn.BatchNorm2d(ch[i]),
+                    nn.LeakyReLU(LRELU_SLOPE, inplace=True)]
+        enc += [nn.Conv2d(ch[-1], 100, 4, 1, 0, bias=False), nn.BatchNorm2d(100), nn.LeakyReLU(LRELU_SLOPE, inplace=True)]
+        dec = [nn.ConvTranspose2d(100, ch[-1], 4, 1, 0, bias=False), nn.BatchNorm2d(ch[-1]), nn.ReLU(True)]
+        for i in range(len(ch) - 1, 0, -1):
+            dec += [nn.ConvTranspose2d(ch[i], ch[i - 1], 4, 2, 1, bias=False), nn.BatchNorm2d(ch[i - 1]), nn.ReLU(True)]
+        dec += [nn.ConvTranspose2d(ch[0], 3, 4, 2, 1, bias=False), nn.Sigmoid()]
+        self.encoder = nn.Sequential(*enc)
+        self.decoder = nn.Sequential(*dec)
+        self._packed = _new_packed()
+
+    def forward(self, input):
+        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return _GenFn.apply(self, input, *list(self.parameters()))
+        out, _ = generator_forward(self, input, save=False)
+        return out

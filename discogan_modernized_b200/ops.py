@@ -1,0 +1,309 @@
+"""Tensor-level wrappers over the C ABI (include/discogan_b200.h).
+
+Every function launches on ``torch.cuda.current_stream()`` and never synchronises.  Inputs are
+checked (device, dtype, contiguity) and a wrong argument raises ``ValueError``/``KernelError``
+synchronously -- there is no CPU fallback.
+"""
+import torch
+
+from ._lib import KernelError, check, lib
+
+ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (discogan_modernized_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+_scratch = {}
+
+
+def scratch(kind, nbytes, device):
+    """Grow-only per-device scratch buffers (wgrad workspace, BN partials, reduction partials)."""
+    key = (kind, device)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def device_check():
+    check(lib().dg_device_check(), "dg_device_check")
+
+
+# ---- weights / layout ---------------------------------------------------------------------
+def pack_weights(w, want_wd=True, want_wu=True):
+    """fp32 [Cs,Cb,4,4] -> (bf16 Wd [Cs,16,Cb], bf16 Wu [Cb,16,Cs])."""
+    Cs, Cb = w.shape[0], w.shape[1]
+    wd = torch.empty(Cs, 16, Cb, dtype=BF16, device=w.device) if want_wd else None
+    wu = torch.empty(Cb, 16, Cs, dtype=BF16, device=w.device) if want_wu else None
+    check(lib().dg_pack_weights(_ptr(w, F32, "w"), _ptr(wd), _ptr(wu), Cs, Cb, _stream()), "dg_pack_weights")
+    return wd, wu
+
+
+def nhwc_to_nchw_f32(x):
+    B, H, W, C = x.shape
+    y = torch.empty(B, C, H, W, dtype=F32, device=x.device)
+    check(lib().dg_nhwc_bf16_to_nchw_f32(_ptr(x, BF16, "x"), _ptr(y), B, H * W, C, _stream()), "dg_nhwc_bf16_to_nchw_f32")
+    return y
+
+
+def nchw_f32_to_nhwc(x):
+    B, C, H, W = x.shape
+    y = torch.empty(B, H, W, C, dtype=BF16, device=x.device)
+    check(lib().dg_nchw_f32_to_nhwc_bf16(_ptr(x, F32, "x"), _ptr(y), B, H * W, C, _stream()), "dg_nchw_f32_to_nhwc_bf16")
+    return y
+
+
+# ---- tensor-core convolutions ---------------------------------------------------------------
+_conv_impl = "tc"  # "simt" only for on-device debugging (DISCOGAN_B200_CONV=simt)
+
+
+def set_conv_impl(name):
+    global _conv_impl
+    if name not in ("tc", "simt"):
+        raise ValueError(name)
+    _conv_impl = name
+
+
+def conv_down(big, wd):
+    """[B,H,W,Cb] x Wd[Cs,16,Cb] -> [B,H/2,W/2,Cs]  (Conv2d 4x4 s2 p1 forward / ConvTranspose2d dgrad)."""
+    B, H, W, Cb = big.shape
+    Cs = wd.shape[0]
+    out = torch.empty(B, H // 2, W // 2, Cs, dtype=BF16, device=big.device)
+    fn = lib().dg_conv4x4s2_fprop if _conv_impl == "tc" else lib().dg_simt_conv4x4s2_fprop
+    check(fn(_ptr(big, BF16, "big"), _ptr(wd, BF16, "wd"), _ptr(out), B, H, W, Cb, Cs, _stream()), "dg_conv4x4s2_fprop")
+    return out
+
+
+def conv_up(small, wu):
+    """[B,Hs,Ws,Cs] x Wu[Cb,16,Cs] -> [B,2Hs,2Ws,Cb]  (Conv2d dgrad / ConvTranspose2d 4x4 s2 p1 forward)."""
+    B, Hs, Ws, Cs = small.shape
+    Cb = wu.shape[0]
+    out = torch.empty(B, 2 * Hs, 2 * Ws, Cb, dtype=BF16, device=small.device)
+    fn = lib().dg_conv4x4s2_dgrad if _conv_impl == "tc" else lib().dg_simt_conv4x4s2_dgrad
+    check(fn(_ptr(small, BF16, "small"), _ptr(wu, BF16, "wu"), _ptr(out), B, Hs, Ws, Cs, Cb, _stream()),
+          "dg_conv4x4s2_dgrad")
+    return out
+
+
+def conv_wgrad(small, big, dw, beta=1.0):
+    """dw[Cs,Cb,4,4] = beta*dw + sum_pixels small (x) shifted big."""
+    B, Hs, Ws, Cs = small.shape
+    Cb = big.shape[3]
+    if tuple(dw.shape) != (Cs, Cb, 4, 4):
+        raise ValueError(f"dw shape {tuple(dw.shape)} != {(Cs, Cb, 4, 4)}")
+    if _conv_impl == "simt":
+        check(lib().dg_simt_conv4x4s2_wgrad(_ptr(small, BF16, "small"), _ptr(big, BF16, "big"), _ptr(dw, F32, "dw"),
+                                            beta, B, Hs, Ws, Cs, Cb, _stream()), "dg_simt_conv4x4s2_wgrad")
+        return
+    need = lib().dg_conv4x4s2_wgrad_workspace(B, Hs, Ws, Cs, Cb)
+    if need == 0:
+        raise KernelError(f"wgrad: unsupported shape B={B} Hs={Hs} Ws={Ws} Cs={Cs} Cb={Cb}")
+    ws = scratch("wgrad", need, small.device)
+    check(lib().dg_conv4x4s2_wgrad(_ptr(small, BF16, "small"), _ptr(big, BF16, "big"), _ptr(dw, F32, "dw"), beta, B, Hs,
+                                   Ws, Cs, Cb, ws.data_ptr(), ws.numel(), _stream()), "dg_conv4x4s2_wgrad")
+
+
+# ---- image-side 3-channel layers ---------------------------------------------------------------
+def conv_c3_in_fwd(x, w, slope=0.2):
+    B, _, S, _ = x.shape
+    y = torch.empty(B, S // 2, S // 2, 64, dtype=BF16, device=x.device)
+    check(lib().dg_conv_c3_in_fwd(_ptr(x, F32, "x"), _ptr(w, F32, "w"), _ptr(y), B, S, slope, _stream()), "dg_conv_c3_in_fwd")
+    return y
+
+
+def conv_c3_in_bwd(x, w, y, dy, dx=None, dx_accumulate=False, dw=None, slope=0.2):
+    B, _, S, _ = x.shape
+    check(lib().dg_conv_c3_in_bwd(_ptr(x, F32, "x"), _ptr(w, F32, "w"), _ptr(y, BF16, "y"), _ptr(dy, BF16, "dy"),
+                                  _ptr(dx, F32, "dx"), int(dx_accumulate), _ptr(dw, F32, "dw"), B, S, slope, _stream()),
+          "dg_conv_c3_in_bwd")
+
+
+def convT_c3_out_fwd(x, w):
+    B, Hs, _, _ = x.shape
+    S = 2 * Hs
+    y = torch.empty(B, 3, S, S, dtype=F32, device=x.device)
+    check(lib().dg_convT_c3_out_fwd(_ptr(x, BF16, "x"), _ptr(w, F32, "w"), _ptr(y), B, S, _stream()), "dg_convT_c3_out_fwd")
+    return y
+
+
+def convT_c3_out_bwd(x, w, y, dy, want_dx=True, dw=None):
+    B, _, S, _ = y.shape
+    dx = torch.empty_like(x) if want_dx else None
+    check(lib().dg_convT_c3_out_bwd(_ptr(x, BF16, "x"), _ptr(w, F32, "w"), _ptr(y, F32, "y"), _ptr(dy, F32, "dy"),
+                                    _ptr(dx), _ptr(dw, F32, "dw"), B, S, _stream()), "dg_convT_c3_out_bwd")
+    return dx
+
+
+# ---- FC heads -------------------------------------------------------------------------------
+def fc_down(big2d, wd2d, out_f32=False):
+    """[B,K] x Wd[Ns,K] -> [B,Ns]."""
+    B, K = big2d.shape
+    Ns = wd2d.shape[0]
+    out = torch.empty(B, Ns, dtype=F32 if out_f32 else BF16, device=big2d.device)
+    check(lib().dg_fc_down(_ptr(big2d, BF16, "big"), _ptr(wd2d, BF16, "wd"), _ptr(out), int(out_f32), B, Ns, K, _stream()),
+          "dg_fc_down")
+    return out
+
+
+def fc_up(small2d, wd2d):
+    """[B,Ns] x Wd[Ns,K] -> [B,K] bf16."""
+    B, Ns = small2d.shape
+    K = wd2d.shape[1]
+    f32 = small2d.dtype == F32
+    out = torch.empty(B, K, dtype=BF16, device=small2d.device)
+    check(lib().dg_fc_up(_ptr(small2d, F32 if f32 else BF16, "small"), int(f32), _ptr(wd2d, BF16, "wd"), _ptr(out), B, Ns, K,
+                         _stream()), "dg_fc_up")
+    return out
+
+
+def fc_wgrad(small2d, big2d, dw, beta=1.0):
+    """dw[Ns,C,4,4] = beta*dw + small^T . big, big = [B,16*C]."""
+    B, Ns = small2d.shape
+    C = big2d.shape[1] // 16
+    if tuple(dw.shape) != (Ns, C, 4, 4):
+        raise ValueError(f"dw shape {tuple(dw.shape)} != {(Ns, C, 4, 4)}")
+    f32 = small2d.dtype == F32
+    check(lib().dg_fc_wgrad(_ptr(small2d, F32 if f32 else BF16, "small"), int(f32), _ptr(big2d, BF16, "big"),
+                            _ptr(dw, F32, "dw"), beta, B, Ns, C, _stream()), "dg_fc_wgrad")
+
+
+# ---- BatchNorm + activation -----------------------------------------------------------------
+def _bn_scratch(P, C, device):
+    n = lib().dg_bn_scratch_floats(P, C)
+    return scratch("bn", 4 * n, device)
+
+
+def bn_stats(z2d, gamma, beta, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
+    """Training statistics of z[P,C] -> stats fp32 [4,C] = (mean, invstd, scale, shift); updates running stats."""
+    P, C = z2d.shape
+    stats = torch.empty(4, C, dtype=F32, device=z2d.device)
+    sc = _bn_scratch(P, C, z2d.device)
+    check(lib().dg_bn_stats(_ptr(z2d, BF16, "z"), P, C, _ptr(gamma, F32, "gamma"), _ptr(beta, F32, "beta"), eps, momentum,
+                            _ptr(stats), _ptr(running_mean, F32, "running_mean"), _ptr(running_var, F32, "running_var"),
+                            sc.data_ptr(), _stream()), "dg_bn_stats")
+    return stats
+
+
+def bn_eval_stats(gamma, beta, running_mean, running_var, eps=1e-5):
+    C = gamma.numel()
+    stats = torch.zeros(4, C, dtype=F32, device=gamma.device)
+    check(lib().dg_bn_eval_coeffs(_ptr(gamma, F32), _ptr(beta, F32), _ptr(running_mean, F32), _ptr(running_var, F32), eps,
+                                  C, _ptr(stats), _stream()), "dg_bn_eval_coeffs")
+    return stats
+
+
+def bn_act_fwd(z2d, stats, act, slope=0.2, out=None):
+    P, C = z2d.shape
+    y = torch.empty_like(z2d) if out is None else out
+    check(lib().dg_bn_act_fwd(_ptr(z2d, BF16, "z"), _ptr(y, BF16, "y"), P, C, _ptr(stats, F32, "stats"), act, slope, _stream()),
+          "dg_bn_act_fwd")
+    return y
+
+
+def bn_act_bwd(dy2d, y2d, z2d, stats, gamma, act, slope=0.2, dgamma=None, dbeta=None, grad_beta=1.0, dy2=None,
+               bcast=None, bcast_coef=0.0):
+    """Backward of y = act(BN_train(z)); returns dz.  dgamma/dbeta (fp32 [C]) are updated as
+    grad_beta*old + new when given."""
+    P, C = z2d.shape
+    dz = torch.empty_like(z2d)
+    coefs = torch.empty(3, C, dtype=F32, device=z2d.device)
+    sc = _bn_scratch(P, C, z2d.device)
+    bcast_rows = 0
+    if bcast is not None:
+        bcast_rows = bcast.numel() // C
+    check(lib().dg_bn_act_bwd(_ptr(dy2d, BF16, "dy"), _ptr(dy2, BF16, "dy2"), _ptr(bcast, F32, "bcast"), bcast_coef, bcast_rows,
+                              _ptr(y2d, BF16, "y"), _ptr(z2d, BF16, "z"), _ptr(stats, F32, "stats"), _ptr(gamma, F32, "gamma"),
+                              P, C, act, slope, _ptr(dgamma, F32, "dgamma"), _ptr(dbeta, F32, "dbeta"), grad_beta, _ptr(dz),
+                              _ptr(coefs), sc.data_ptr(), _stream()), "dg_bn_act_bwd")
+    return dz
+
+
+# ---- losses -----------------------------------------------------------------------------------
+def _red_scratch(device):
+    return scratch("reduce", 4 * lib().dg_reduce_scratch_floats(), device)
+
+
+def gan_bce_fwd(logit_real, logit_fake, out2):
+    """out2[0] = dis_loss, out2[1] = gen_loss; returns (p_real, p_fake)."""
+    B = logit_real.numel()
+    p_real, p_fake = torch.empty_like(logit_real), torch.empty_like(logit_fake)
+    check(lib().dg_gan_bce_fwd(_ptr(logit_real, F32), _ptr(logit_fake, F32), B, _ptr(p_real), _ptr(p_fake), _ptr(out2, F32),
+                               _stream()), "dg_gan_bce_fwd")
+    return p_real, p_fake
+
+
+def gan_bce_bwd(p_real, p_fake, g_dis, g_gen, want_real=True, want_fake=True):
+    B = p_real.numel()
+    dr = torch.empty_like(p_real) if want_real else None
+    df = torch.empty_like(p_fake) if want_fake else None
+    check(lib().dg_gan_bce_bwd(_ptr(p_real, F32), _ptr(p_fake, F32), B, g_dis, g_gen, _ptr(dr), _ptr(df), _stream()),
+          "dg_gan_bce_bwd")
+    return dr, df
+
+
+def sigmoid_fwd(x):
+    y = torch.empty_like(x)
+    check(lib().dg_sigmoid_fwd(_ptr(x, F32), _ptr(y), x.numel(), _stream()), "dg_sigmoid_fwd")
+    return y
+
+
+def sigmoid_bwd(y, dy):
+    dx = torch.empty_like(y)
+    check(lib().dg_sigmoid_bwd(_ptr(y, F32), _ptr(dy, F32), _ptr(dx), y.numel(), _stream()), "dg_sigmoid_bwd")
+    return dx
+
+
+def mse_fwd(a, b, out):
+    """out[0] = mean((a-b)^2); out is a 1-element fp32 view."""
+    check(lib().dg_mse_fwd(_ptr(a, F32, "a"), _ptr(b, F32, "b"), a.numel(), _ptr(out, F32), _red_scratch(a.device).data_ptr(),
+                           _stream()), "dg_mse_fwd")
+
+
+def mse_bwd(a, b, g, da=None, accumulate=False):
+    """da (+)= g * d mean((a-b)^2) / da."""
+    if da is None:
+        da = torch.empty_like(a)
+        accumulate = False
+    check(lib().dg_mse_bwd(_ptr(a, F32, "a"), _ptr(b, F32, "b"), a.numel(), g, _ptr(da, F32, "da"), int(accumulate), _stream()),
+          "dg_mse_bwd")
+    return da
+
+
+def fm_fwd(real, fake, out, accumulate, want_diff=True):
+    """One feature map (NHWC bf16, same shape): out[0] (+)= mean((mean_b real - mean_b fake)^2); returns diff."""
+    B = real.shape[0]
+    n = real.numel() // B
+    diff = torch.empty(n, dtype=F32, device=real.device) if want_diff else None
+    check(lib().dg_fm_fwd(_ptr(real, BF16, "real"), _ptr(fake, BF16, "fake"), B, n, _ptr(diff), _ptr(out, F32),
+                          int(accumulate), _red_scratch(real.device).data_ptr(), _stream()), "dg_fm_fwd")
+    return diff
+
+
+def fm_bwd(diff, B, shape, g):
+    """d(g*fm)/d fake as a bf16 tensor of `shape` (negate g for the real branch)."""
+    n = diff.numel()
+    dfeat = torch.empty(shape, dtype=BF16, device=diff.device)
+    check(lib().dg_fm_bwd(_ptr(diff, F32), B, n, g, _ptr(dfeat), _stream()), "dg_fm_bwd")
+    return dfeat
+
+
+# ---- optimiser --------------------------------------------------------------------------------
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(lib().dg_adam_step(_ptr(p, F32, "p"), _ptr(g, F32, "g"), _ptr(m, F32, "m"), _ptr(v, F32, "v"), p.numel(), lr, beta1,
+                             beta2, eps, weight_decay, step, grad_scale, _stream()), "dg_adam_step")

@@ -1,0 +1,283 @@
+"""The DiscoGAN train step on the B200 kernels (single GPU and data parallel).
+
+Implements the body of the reference loop -- ``image_translation.py:335-390`` (single device),
+``distributed_image_translation.py:465-518`` (DDP) and the ``angle_pairing.py:291-346`` variant --
+as one hand-scheduled forward/backward over the kernel engines in ``model.py``:
+
+* all eight forwards run every iteration (BatchNorm running statistics advance exactly as in the
+  reference), but only the gradients that reach an optimiser step are computed: a D step back-props
+  the two discriminators only, a G step back-props the generators and the *data* path of the
+  discriminators' fake passes (the reference computes and discards the rest);
+* GAN-BCE, reconstruction-MSE and feature-matching losses are fused kernels; loss weights are host
+  constants so no autograd graph is built;
+* parameters, gradients and Adam moments of each network live in flat fp32 buffers: Adam is one
+  kernel per network and the data-parallel exchange is one NCCL all-reduce per network, issued on a
+  side stream as soon as that network's last backward pass has been enqueued (overlapping the
+  remaining backward work); gradients are averaged over ranks, BatchNorm statistics stay per rank,
+  the learning rate is not scaled (``distributed_image_translation.py:396-427`` semantics with the
+  ``broadcast_buffers`` crash of SURVEY.md F4 avoided).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .model import (Discriminator, Generator, discriminator_backward, discriminator_forward, generator_backward,
+                    generator_forward)
+
+LOSS_NAMES = ("dis_loss_A", "gen_loss_A", "dis_loss_B", "gen_loss_B", "fm_loss_A", "fm_loss_B", "recon_loss_A",
+              "recon_loss_B")
+_ALIGN = 64  # floats; keeps every parameter view 256-byte aligned
+
+
+class FlatNet:
+    """Flat fp32 parameter / gradient / Adam-moment buffers of one network; ``p.data`` and ``p.grad``
+    of every parameter become views into them (registration order, ``image_translation.py:272-273``)."""
+
+    def __init__(self, net):
+        self.net = net
+        params = list(net.parameters())
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = total
+        self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.steps = 0
+        for p, o in zip(params, offs):
+            view = self.flat_p[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_g[o:o + p.numel()].view(p.shape)
+        self.params, self.offsets = params, offs
+        net._packed.invalidate()
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+        for p, o in zip(self.params, self.offsets):  # re-attach in case someone set .grad = None
+            if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * o:
+                p.grad = self.flat_g[o:o + p.numel()].view(p.shape)
+
+    def adam(self, lr, beta1, beta2, eps, weight_decay, grad_scale):
+        self.steps += 1
+        ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr, beta1, beta2, eps, weight_decay,
+                      self.steps, grad_scale)
+        self.net._packed.invalidate()
+
+
+class GradReducer:
+    """Average flat gradient buffers over the data-parallel group.  CUDA: NCCL all-reduce on a side
+    stream ordered after the producing kernels, joined before Adam.  CPU tensors (gloo, tests): blocking."""
+
+    def __init__(self, group=None):
+        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.group = group
+        self.world = dist.get_world_size(group) if self.enabled else 1
+        self._stream = None
+        self._pending = []
+
+    def launch(self, flat_g):
+        """Start summing flat_g over ranks (the 1/world factor is folded into Adam's grad_scale)."""
+        if not self.enabled:
+            return
+        if flat_g.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream()
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                self._stream.wait_event(ready)
+                dist.all_reduce(flat_g, op=dist.ReduceOp.SUM, group=self.group)
+                done = torch.cuda.Event()
+                done.record(self._stream)
+            self._pending.append(done)
+        else:
+            dist.all_reduce(flat_g, op=dist.ReduceOp.SUM, group=self.group)
+
+    def join(self):
+        for ev in self._pending:
+            torch.cuda.current_stream().wait_event(ev)
+        self._pending = []
+
+    @property
+    def grad_scale(self):
+        return 1.0 / self.world
+
+    def broadcast_params(self, flat_nets):
+        """Rank 0's weights to everyone once at start (DDP constructor semantics, C2)."""
+        if not self.enabled:
+            return
+        for fn in flat_nets:
+            dist.broadcast(fn.flat_p, src=0, group=self.group)
+            fn.net._packed.invalidate()
+
+
+def loss_coefficients(model_arch, rate):
+    """d(gen_loss)/d(component) for image_translation.py:370-382.  Returns dict with keys
+    gen_A/fm_A (through D_A's fake pass), gen_B/fm_B (through D_B's fake pass), recon_A, recon_B,
+    and the D-step flags dis_A/dis_B."""
+    if model_arch == "discogan":
+        return dict(gen_A=0.1 * (1 - rate), fm_A=0.9 * (1 - rate), gen_B=0.1 * (1 - rate), fm_B=0.9 * (1 - rate),
+                    recon_A=rate, recon_B=rate, dis_A=1.0, dis_B=1.0)
+    if model_arch == "recongan":  # gen_loss = gen_loss_A_total = (fm_B*.9 + gen_B*.1)(1-rate) + recon_A*rate
+        return dict(gen_A=0.0, fm_A=0.0, gen_B=0.1 * (1 - rate), fm_B=0.9 * (1 - rate), recon_A=rate, recon_B=0.0,
+                    dis_A=0.0, dis_B=1.0)
+    if model_arch == "gan":       # gen_loss = gen_B*.1 + fm_B*.9
+        return dict(gen_A=0.0, fm_A=0.0, gen_B=0.1, fm_B=0.9, recon_A=0.0, recon_B=0.0, dis_A=0.0, dis_B=1.0)
+    raise ValueError(f"unknown model_arch {model_arch!r}")
+
+
+class DiscoGANTrainer:
+    """Owns G_A, G_B, D_A, D_B and performs reference-equivalent iterations with ``step(A, B)``.
+
+    variant='angle_pairing' skips the first feature map in the FM loss and defaults both rates to 0.9
+    (``angle_pairing.py:55-57,115``)."""
+
+    def __init__(self, image_size=512, device="cuda", model_arch="discogan", learning_rate=2e-4, beta1=0.5,
+                 beta2=0.999, weight_decay=1e-5, update_interval=3, gan_curriculum=10000, starting_rate=None,
+                 default_rate=None, variant="image_translation", seed=None, nets=None, process_group=None):
+        ops.device_check()
+        self.device = torch.device(device)
+        self.image_size = image_size
+        self.model_arch = model_arch
+        loss_coefficients(model_arch, 0.5)  # validates
+        angle = variant == "angle_pairing"
+        self.fm_skip_first = angle
+        self.starting_rate = (0.9 if angle else 0.01) if starting_rate is None else starting_rate
+        self.default_rate = (0.9 if angle else 0.5) if default_rate is None else default_rate
+        self.update_interval, self.gan_curriculum = update_interval, gan_curriculum
+        self.lr, self.beta1, self.beta2, self.eps, self.weight_decay = learning_rate, beta1, beta2, 1e-8, weight_decay
+        if nets is None:
+            if seed is not None:
+                torch.manual_seed(seed)
+            nets = [Generator(extra_layers=True, image_size=image_size), Generator(extra_layers=True, image_size=image_size),
+                    Discriminator(image_size=image_size), Discriminator(image_size=image_size)]
+        self.G_A, self.G_B, self.D_A, self.D_B = [n.to(self.device).train() for n in nets]
+        self.flat = {n: FlatNet(n) for n in (self.G_A, self.G_B, self.D_A, self.D_B)}
+        self.reducer = GradReducer(process_group)
+        self.reducer.broadcast_params(self.flat.values())
+        self.loss_buf = torch.zeros(len(LOSS_NAMES), dtype=torch.float32, device=self.device)
+        self.iters = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _disc_pair(self, D, real_img, fake_img, slot, save_real, save_fake):
+        """Both passes of one discriminator + its BCE and FM losses (image_translation.py:353-364)."""
+        lr_, feats_r, ctx_r = discriminator_forward(D, real_img, save=save_real)
+        lf_, feats_f, ctx_f = discriminator_forward(D, fake_img, save=save_fake)
+        buf = self.loss_buf
+        p_real, p_fake = ops.gan_bce_fwd(lr_, lf_, buf[2 * slot:2 * slot + 2])
+        fm_out = buf[4 + slot:5 + slot]
+        diffs = []
+        first = True
+        for i, (fr, ff) in enumerate(zip(feats_r, feats_f)):
+            if self.fm_skip_first and i == 0:
+                diffs.append(None)
+                continue
+            diffs.append(ops.fm_fwd(fr, ff, fm_out, accumulate=not first))
+            first = False
+        if first:
+            fm_out.zero_()
+        return dict(ctx_r=ctx_r, ctx_f=ctx_f, p_real=p_real, p_fake=p_fake, diffs=diffs, feats_f=feats_f)
+
+    def step(self, A, B):
+        """One iteration on a batch pair (fp32 NCHW on the trainer's device).  Returns True if it was a
+        discriminator step.  Losses of the iteration are in ``self.loss_buf`` (see ``losses()``)."""
+        is_dis = self.iters % self.update_interval == 0
+        rate = self.starting_rate if self.iters < self.gan_curriculum else self.default_rate
+        co = loss_coefficients(self.model_arch, rate)
+        G_A, G_B, D_A, D_B = self.G_A, self.G_B, self.D_A, self.D_B
+        save_g = not is_dis
+        AB, c_gb1 = generator_forward(G_B, A, save=save_g)       # A -> B
+        BA, c_ga1 = generator_forward(G_A, B, save=save_g)       # B -> A
+        ABA, c_ga2 = generator_forward(G_A, AB, save=save_g)     # A -> B -> A
+        BAB, c_gb2 = generator_forward(G_B, BA, save=save_g)     # B -> A -> B
+        ops.mse_fwd(ABA, A, self.loss_buf[6:7])
+        ops.mse_fwd(BAB, B, self.loss_buf[7:8])
+        da = self._disc_pair(D_A, A, BA, 0, save_real=is_dis, save_fake=True)
+        db = self._disc_pair(D_B, B, AB, 1, save_real=is_dis, save_fake=True)
+
+        red = self.reducer
+        if is_dis:
+            stepped = []
+            for D, d, c in ((D_A, da, co["dis_A"]), (D_B, db, co["dis_B"])):
+                if c == 0.0:
+                    continue
+                self.flat[D].zero_grad()
+                dlr, dlf = ops.gan_bce_bwd(d["p_real"], d["p_fake"], c, 0.0)
+                discriminator_backward(D, d["ctx_r"], dlr, need_dx=False, need_wgrad=True)
+                discriminator_backward(D, d["ctx_f"], dlf, need_dx=False, need_wgrad=True)
+                red.launch(self.flat[D].flat_g)
+                stepped.append(D)
+        else:
+            use_a = co["gen_A"] != 0.0 or co["fm_A"] != 0.0      # losses through D_A(BA): reach G_A pass 1
+            use_b = co["gen_B"] != 0.0 or co["fm_B"] != 0.0      # losses through D_B(AB): reach G_B pass 1
+            stepped = []
+            if use_b or co["recon_A"] != 0.0:
+                stepped.append(G_B)
+            if use_a or co["recon_B"] != 0.0 or co["recon_A"] != 0.0:
+                stepped.append(G_A)
+            if co["recon_B"] != 0.0 and G_B not in stepped:
+                stepped.append(G_B)
+            for G in stepped:
+                self.flat[G].zero_grad()
+            # ---- everything that ends in G_B's first pass (input A): D_B(AB) and G_A(AB) -> ABA
+            dAB = None
+            if use_b:
+                dAB = self._disc_fake_backward(D_B, db, co["gen_B"], co["fm_B"], AB.shape[0])
+            if co["recon_A"] != 0.0:
+                dABA = ops.mse_bwd(ABA, A, co["recon_A"])
+                dAB = generator_backward(G_A, c_ga2, dABA, need_dx=True, need_wgrad=True, dx_out=dAB,
+                                         dx_accumulate=dAB is not None)
+            if dAB is not None:
+                generator_backward(G_B, c_gb1, dAB, need_dx=False, need_wgrad=True)
+            # ---- everything that ends in G_A's first pass (input B): D_A(BA) and G_B(BA) -> BAB
+            dBA = None
+            if use_a:
+                dBA = self._disc_fake_backward(D_A, da, co["gen_A"], co["fm_A"], BA.shape[0])
+            if co["recon_B"] != 0.0:
+                dBAB = ops.mse_bwd(BAB, B, co["recon_B"])
+                dBA = generator_backward(G_B, c_gb2, dBAB, need_dx=True, need_wgrad=True, dx_out=dBA,
+                                         dx_accumulate=dBA is not None)
+            if G_B in stepped:
+                red.launch(self.flat[G_B].flat_g)                # G_B is complete: overlap with G_A's last pass
+            if dBA is not None:
+                generator_backward(G_A, c_ga1, dBA, need_dx=False, need_wgrad=True)
+            if G_A in stepped:
+                red.launch(self.flat[G_A].flat_g)
+        red.join()
+        for n in stepped:
+            self.flat[n].adam(self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, red.grad_scale)
+        self.iters += 1
+        return is_dis
+
+    def _disc_fake_backward(self, D, d, c_gen, c_fm, B):
+        """Back-prop c_gen*gen_loss + c_fm*fm_loss through the fake pass of D down to its input image."""
+        _, dlf = ops.gan_bce_bwd(d["p_real"], d["p_fake"], 0.0, c_gen, want_real=False)
+        bcast = []
+        for diff, f in zip(d["diffs"], d["feats_f"]):
+            if diff is None or c_fm == 0.0:
+                bcast.append(None)
+            else:
+                n = diff.numel()
+                bcast.append((diff, -c_fm * 2.0 / (float(n) * float(B))))
+        return discriminator_backward(D, d["ctx_f"], dlf, None, bcast, need_dx=True, need_wgrad=False)
+
+    # ------------------------------------------------------------------------------------------
+    def losses(self):
+        """Host copy of the last iteration's eight logged losses (synchronises)."""
+        return dict(zip(LOSS_NAMES, self.loss_buf.tolist()))
+
+    def log_line(self, total_iterations):
+        """The reference's log format (image_translation.py:394-398; parsed by hyperparameter_search.py:269-271)."""
+        l = self.losses()
+        return (f"Iter [{self.iters - 1}/{total_iterations}] "
+                f"GEN: {l['gen_loss_A']:.4f}/{l['gen_loss_B']:.4f}, "
+                f"FM: {l['fm_loss_A']:.4f}/{l['fm_loss_B']:.4f}, "
+                f"RECON: {l['recon_loss_A']:.4f}/{l['recon_loss_B']:.4f}, "
+                f"DIS: {l['dis_loss_A']:.4f}/{l['dis_loss_B']:.4f}")
+
+    def nets(self):
+        return self.G_A, self.G_B, self.D_A, self.D_B

@@ -1,0 +1,126 @@
+/* discogan_b200.h -- C ABI of libdiscogan_b200.so (hand-written sm_100a kernels for the DiscoGAN train step).
+ *
+ * The reference (fasion-image-generator-project/discogan_modernized) has no FFI: every operation on its hot path
+ * is a PyTorch library call made from model.py / image_translation.py.  Each entry point below names the reference
+ * call site (file:line, relative to the reference tree) whose arithmetic it replaces.  The Python host layer
+ * (discogan_modernized_b200/ops.py) binds these with ctypes; see INTEGRATION.md for the binding a reference
+ * maintainer would add.
+ *
+ * Conventions: raw device pointers, explicit dims, a cudaStream_t; every function returns 0 on success and a
+ * non-zero code otherwise (dg_last_error() gives the message); no allocation, no implicit synchronisation, no
+ * cuDNN/cuBLAS, no CPU fallback.  Activations are NHWC bf16; images at the module boundary are NCHW fp32;
+ * parameters, gradients, statistics and losses are fp32.  "big"/"small" are the two tensors a 4x4 stride-2 layer
+ * connects: big = [B,2Hs,2Ws,Cb], small = [B,Hs,Ws,Cs]; the PyTorch weight viewed as W[Cs][Cb][4][4] is the
+ * Conv2d weight [out=Cs][in=Cb] and equally the ConvTranspose2d weight [in=Cs][out=Cb].
+ */
+#ifndef DISCOGAN_B200_H
+#define DISCOGAN_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* dg_stream_t; /* == cudaStream_t */
+
+enum { DG_ACT_NONE = 0, DG_ACT_LRELU = 1, DG_ACT_RELU = 2 };
+
+/* ---- runtime ---- */
+const char* dg_last_error(void);
+int dg_version(void);
+int dg_device_check(void); /* non-zero unless the current device is sm_100 */
+
+/* ---- weights: fp32 W[Cs][Cb][4][4] -> bf16 Wd[Cs][16][Cb] (K-major for DOWN) and Wu[Cb][16][Cs] (for UP).
+ * Either output may be NULL.  (Parameters: model.py:8-35,80-142.) */
+int dg_pack_weights(const float* w, void* wd, void* wu, int Cs, int Cb, dg_stream_t stream);
+
+/* ---- layout converters for feature maps crossing the module boundary (model.py:69 returns NCHW fp32) ---- */
+int dg_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, dg_stream_t stream);
+int dg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int HW, int C, dg_stream_t stream);
+
+/* ---- tensor-core implicit-GEMM convolutions (tcgen05 + TMEM + TMA) ----
+ * nn.Conv2d(ci,co,4,2,1,bias=False) forward, model.py:11-31,84-103 (cuDNN fprop in the reference) */
+int dg_conv4x4s2_fprop(const void* x_big, const void* wd, void* z_small, int B, int H, int W, int Cb, int Cs,
+                       dg_stream_t stream);
+/* its data gradient (cuDNN bwd-data); also nn.ConvTranspose2d(ci,co,4,2,1) forward, model.py:118-138 */
+int dg_conv4x4s2_dgrad(const void* dz_small, const void* wu, void* dx_big, int B, int Hs, int Ws, int Cs, int Cb,
+                       dg_stream_t stream);
+/* weight gradient (cuDNN bwd-filter): dw[Cs][Cb][4][4] = beta*dw + sum small (x) big; needs a workspace */
+size_t dg_conv4x4s2_wgrad_workspace(int B, int Hs, int Ws, int Cs, int Cb);
+int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
+                       int Cb, void* ws, size_t ws_bytes, dg_stream_t stream);
+/* ConvTranspose2d(4,2,1) aliases: forward == dgrad, dgrad == fprop, wgrad == wgrad(small = x, big = dy) */
+int dg_convT4x4s2_fprop(const void* x_small, const void* wu, void* y_big, int B, int Hs, int Ws, int Cs, int Cb,
+                        dg_stream_t stream);
+int dg_convT4x4s2_dgrad(const void* dy_big, const void* wd, void* dx_small, int B, int H, int W, int Cb, int Cs,
+                        dg_stream_t stream);
+int dg_convT4x4s2_wgrad(const void* x_small, const void* dy_big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
+                        int Cb, void* ws, size_t ws_bytes, dg_stream_t stream);
+
+/* ---- image-side 3-channel layers (direct kernels, fp32 NCHW image <-> bf16 NHWC 64 channels) ----
+ * nn.Conv2d(3,64,4,2,1)+LeakyReLU(0.2), model.py:8-9,80-81 */
+int dg_conv_c3_in_fwd(const float* x, const float* w, void* y, int B, int S, float slope, dg_stream_t stream);
+int dg_conv_c3_in_bwd(const float* x, const float* w, const void* y, const void* dy, float* dx, int dx_accumulate,
+                      float* dw, int B, int S, float slope, dg_stream_t stream);
+/* nn.ConvTranspose2d(64,3,4,2,1)+Sigmoid, model.py:142-143 */
+int dg_convT_c3_out_fwd(const void* x, const float* w, float* y, int B, int S, dg_stream_t stream);
+int dg_convT_c3_out_bwd(const void* x, const float* w, const float* y, const float* dy, void* dx, float* dw, int B,
+                        int S, dg_stream_t stream);
+
+/* ---- 4x4 "valid" heads as skinny products against Wd[Ns][K=16*C] ----
+ * nn.Conv2d(C,100,4,1,0) model.py:107, nn.Conv2d(C,1,4,1,0) model.py:35: small = big . Wd^T          (fc_down)
+ * nn.ConvTranspose2d(100,C,4,1,0) model.py:114:                          big = small . Wd            (fc_up)
+ * wgrad in PyTorch layout [Ns][C][4][4]:                                                            (fc_wgrad) */
+int dg_fc_down(const void* big, const void* wd, void* small, int small_f32, int B, int Ns, int K, dg_stream_t stream);
+int dg_fc_up(const void* small, int small_f32, const void* wd, void* big, int B, int Ns, int K, dg_stream_t stream);
+int dg_fc_wgrad(const void* small, int small_f32, const void* big, float* dw, float beta, int B, int Ns, int C,
+                dg_stream_t stream);
+
+/* ---- BatchNorm2d (+LeakyReLU/ReLU), model.py:12-33,84-140 ----
+ * stats = float[4*C] {mean, invstd, scale, shift}; scratch = float[dg_bn_scratch_floats(P,C)] */
+size_t dg_bn_scratch_floats(long long P, int C);
+int dg_bn_stats(const void* z, long long P, int C, const float* gamma, const float* beta, float eps, float momentum,
+                float* stats, float* running_mean, float* running_var, float* scratch, dg_stream_t stream);
+int dg_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                      float eps, int C, float* stats, dg_stream_t stream);
+int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats, int act, float slope,
+                  dg_stream_t stream);
+int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bcast_coef, long long bcast_rows,
+                  const void* y, const void* z, const float* stats, const float* gamma, long long P, int C, int act,
+                  float slope, float* dgamma, float* dbeta, float grad_beta, void* dz, float* coefs, float* scratch,
+                  dg_stream_t stream);
+
+/* ---- losses ----
+ * nn.Sigmoid (model.py:36) + nn.BCELoss in get_gan_loss, image_translation.py:146-168,268 */
+int dg_gan_bce_fwd(const float* logit_real, const float* logit_fake, int B, float* p_real, float* p_fake, float* out2,
+                   dg_stream_t stream);
+int dg_gan_bce_bwd(const float* p_real, const float* p_fake, int B, float g_dis, float g_gen, float* dlogit_real,
+                   float* dlogit_fake, dg_stream_t stream);
+int dg_sigmoid_fwd(const float* x, float* y, int n, dg_stream_t stream);
+int dg_sigmoid_bwd(const float* y, const float* dy, float* dx, int n, dg_stream_t stream);
+/* nn.MSELoss, image_translation.py:267,349-350 */
+size_t dg_reduce_scratch_floats(void);
+int dg_mse_fwd(const float* a, const float* b, long long n, float* out, float* scratch, dg_stream_t stream);
+int dg_mse_bwd(const float* a, const float* b, long long n, float g, float* da, int accumulate, dg_stream_t stream);
+/* get_fm_loss, image_translation.py:136-144 (one feature map per call; accumulate sums the layers) */
+int dg_fm_fwd(const void* real, const void* fake, int B, long long n, float* diff, float* out, int accumulate,
+              float* scratch, dg_stream_t stream);
+int dg_fm_bwd(const float* diff, int B, long long n, float g, void* dfeat, dg_stream_t stream);
+
+/* ---- optim.Adam(lr, betas, weight_decay=1e-5), image_translation.py:275-287 ---- */
+int dg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int step, float grad_scale, dg_stream_t stream);
+
+/* ---- debug-only SIMT versions of the tensor-core convolutions (never the product path) ---- */
+int dg_simt_conv4x4s2_fprop(const void* x, const void* wd, void* z, int B, int H, int W, int Cb, int Cs,
+                            dg_stream_t stream);
+int dg_simt_conv4x4s2_dgrad(const void* dz, const void* wu, void* dx, int B, int Hs, int Ws, int Cs, int Cb,
+                            dg_stream_t stream);
+int dg_simt_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
+                            int Cb, dg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISCOGAN_B200_H */

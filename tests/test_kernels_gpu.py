@@ -1,0 +1,315 @@
+"""Per-kernel parity on the GPU: every C-ABI kernel against the same op in stock fp32 PyTorch
+(cuDNN with TF32 disabled) on identical inputs.  bf16-operand / fp32-accumulate kernels are compared on
+bf16-rounded inputs, so the only differences are accumulation order and the final bf16 rounding of the
+output (rel-L2 tolerance 4e-3, SURVEY.md F9 measured 2.4e-3 for bf16 operands + fp32 outputs)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from discogan_modernized_b200 import ops
+    ops.device_check()
+    yield
+
+
+def ops_mod():
+    from discogan_modernized_b200 import ops
+    return ops
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, generator=g, device="cuda") * scale
+
+
+def to_nhwc_bf16(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(BF16)
+
+
+def to_nchw_f32(x_nhwc):
+    return x_nhwc.float().permute(0, 3, 1, 2).contiguous()
+
+
+def test_pack_weights():
+    ops = ops_mod()
+    for Cs, Cb in ((128, 64), (100, 512), (1, 256)):
+        w = rnd(Cs, Cb, 4, 4, seed=Cs)
+        wd, wu = ops.pack_weights(w)
+        assert torch.equal(wd, w.view(Cs, Cb, 16).permute(0, 2, 1).contiguous().to(BF16))
+        assert torch.equal(wu, w.view(Cs, Cb, 16).permute(1, 2, 0).contiguous().to(BF16))
+
+
+def test_layout_roundtrip():
+    ops = ops_mod()
+    x = rnd(3, 40, 6, 10, seed=1)               # NCHW fp32, ragged sizes
+    y = ops.nchw_f32_to_nhwc(x)
+    assert torch.equal(y, to_nhwc_bf16(x))
+    z = ops.nhwc_to_nchw_f32(y)
+    assert torch.equal(z, x.to(BF16).float())
+
+
+CONV_SHAPES = [
+    # B, H(big), Cb, Cs
+    (2, 8, 64, 128),      # deepest 64^2 shape class: 8->4, batch padded inside a tile
+    (4, 16, 128, 256),
+    (3, 32, 64, 128),     # odd batch
+    (2, 64, 64, 128),     # Wt < W rows
+    (1, 256, 64, 128),    # the 512^2 conv2 geometry (Ws = 128 = one tile row)
+    (9, 8, 256, 512),     # batch tiles with remainder, N=512 -> 2 n-tiles
+    (2, 16, 512, 1024),
+]
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,H,Cb,Cs", CONV_SHAPES)
+def test_conv_down(impl, B, H, Cb, Cs):
+    ops = ops_mod()
+    if impl == "simt" and B * H * H * Cs * Cb > 2e10 / 16:
+        pytest.skip("simt reference kernel too slow for this shape")
+    x = rnd(B, Cb, H, H, seed=1).to(BF16)
+    w = (rnd(Cs, Cb, 4, 4, seed=2) / (4 * Cb ** 0.5)).to(BF16).float()
+    ref = F.conv2d(x.float(), w, stride=2, padding=1)
+    wd, _ = ops.pack_weights(w)
+    ops.set_conv_impl(impl)
+    try:
+        out = ops.conv_down(to_nhwc_bf16(x.float()), wd)
+    finally:
+        ops.set_conv_impl("tc")
+    torch.cuda.synchronize()
+    assert rel_l2(to_nchw_f32(out), ref) < 4e-3
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,H,Cb,Cs", CONV_SHAPES)
+def test_conv_up(impl, B, H, Cb, Cs):
+    ops = ops_mod()
+    Hs = H // 2
+    if impl == "simt" and B * H * H * Cs * Cb > 2e10 / 4:
+        pytest.skip("simt reference kernel too slow for this shape")
+    s = rnd(B, Cs, Hs, Hs, seed=3).to(BF16)
+    w = (rnd(Cs, Cb, 4, 4, seed=4) / (2 * Cs ** 0.5)).to(BF16).float()
+    ref = F.conv_transpose2d(s.float(), w, stride=2, padding=1)
+    _, wu = ops.pack_weights(w)
+    ops.set_conv_impl(impl)
+    try:
+        out = ops.conv_up(to_nhwc_bf16(s.float()), wu)
+    finally:
+        ops.set_conv_impl("tc")
+    torch.cuda.synchronize()
+    assert rel_l2(to_nchw_f32(out), ref) < 4e-3
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,H,Cb,Cs", CONV_SHAPES)
+def test_conv_wgrad(impl, B, H, Cb, Cs):
+    ops = ops_mod()
+    Hs = H // 2
+    if impl == "simt" and B * H * H * Cs * Cb > 2e10 / 16:
+        pytest.skip("simt reference kernel too slow for this shape")
+    big = rnd(B, Cb, H, H, seed=5).to(BF16)
+    small = rnd(B, Cs, Hs, Hs, seed=6).to(BF16)
+    ref = torch.nn.grad.conv2d_weight(big.float(), (Cs, Cb, 4, 4), small.float(), stride=2, padding=1)
+    dw = torch.full((Cs, Cb, 4, 4), 0.5, device="cuda")
+    ops.set_conv_impl(impl)
+    try:
+        ops.conv_wgrad(to_nhwc_bf16(small.float()), to_nhwc_bf16(big.float()), dw, beta=1.0)
+    finally:
+        ops.set_conv_impl("tc")
+    torch.cuda.synchronize()
+    assert rel_l2(dw - 0.5, ref) < 1e-3
+    dw2 = torch.full((Cs, Cb, 4, 4), 7.0, device="cuda")
+    ops.conv_wgrad(to_nhwc_bf16(small.float()), to_nhwc_bf16(big.float()), dw2, beta=0.0)
+    assert rel_l2(dw2, ref) < 1e-3
+
+
+@pytest.mark.parametrize("B,S", [(2, 16), (3, 64), (1, 128)])
+def test_conv_c3_in(B, S):
+    ops = ops_mod()
+    x = torch.rand(B, 3, S, S, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    w = rnd(64, 3, 4, 4, seed=2, scale=0.2)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    ref = F.leaky_relu(F.conv2d(xr, wr, stride=2, padding=1), 0.2)
+    y = ops.conv_c3_in_fwd(x, w)
+    assert rel_l2(to_nchw_f32(y), ref) < 4e-3
+    dy = rnd(B, 64, S // 2, S // 2, seed=3).to(BF16)
+    # backward reference evaluated with the kernel's own (bf16) activation signs
+    mask = torch.where(to_nchw_f32(y) > 0, 1.0, 0.2)
+    z = F.conv2d(xr, wr, stride=2, padding=1)
+    z.backward(dy.float() * mask)
+    dx = torch.empty_like(x)
+    dw = torch.zeros_like(w)
+    ops.conv_c3_in_bwd(x, w, y, to_nhwc_bf16(dy.float()), dx, False, dw)
+    assert rel_l2(dx, xr.grad) < 1e-4
+    assert rel_l2(dw, wr.grad) < 1e-4
+    dx2 = dx.clone()
+    ops.conv_c3_in_bwd(x, w, y, to_nhwc_bf16(dy.float()), dx2, True, None)
+    assert rel_l2(dx2, 2 * xr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,S", [(2, 16), (3, 64), (1, 128)])
+def test_convT_c3_out(B, S):
+    ops = ops_mod()
+    x = rnd(B, 64, S // 2, S // 2, seed=1).to(BF16)
+    w = rnd(64, 3, 4, 4, seed=2, scale=0.1)
+    xr = x.float().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    ref = torch.sigmoid(F.conv_transpose2d(xr, wr, stride=2, padding=1))
+    y = ops.convT_c3_out_fwd(to_nhwc_bf16(x.float()), w)
+    assert rel_l2(y, ref) < 1e-5
+    dy = rnd(B, 3, S, S, seed=3)
+    ref.backward(dy)
+    dw = torch.zeros_like(w)
+    dx = ops.convT_c3_out_bwd(to_nhwc_bf16(x.float()), w, y, dy, True, dw)
+    assert rel_l2(to_nchw_f32(dx), xr.grad) < 4e-3
+    assert rel_l2(dw, wr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("B,Ns,C", [(4, 100, 512), (64, 100, 512), (5, 1, 512), (32, 100, 2048), (2, 1, 2048)])
+def test_fc_heads(B, Ns, C):
+    ops = ops_mod()
+    K = 16 * C
+    w = (rnd(Ns, C, 4, 4, seed=1) / K ** 0.5)
+    wd, _ = ops.pack_weights(w, True, False)
+    wd2 = wd.view(Ns, K)
+    big = rnd(B, 4, 4, C, seed=2).to(BF16)
+    ref = F.conv2d(to_nchw_f32(big), w.to(BF16).float()).view(B, Ns)       # 4x4 valid conv
+    out = ops.fc_down(big.view(B, K), wd2, out_f32=True)
+    assert rel_l2(out, ref) < 1e-4
+    outb = ops.fc_down(big.view(B, K), wd2, out_f32=False)
+    assert rel_l2(outb, ref) < 4e-3
+    small = rnd(B, Ns, seed=3)
+    refu = F.conv_transpose2d(small.to(BF16).float().view(B, Ns, 1, 1), w.to(BF16).float())   # [B,C,4,4]
+    for s in (small.to(BF16), small.to(BF16).float()):
+        up = ops.fc_up(s.contiguous(), wd2).view(B, 4, 4, C)
+        assert rel_l2(to_nchw_f32(up), refu) < 4e-3
+    refw = torch.einsum("bn,bhwc->nchw", small.to(BF16).float(), big.float())
+    dw = torch.full((Ns, C, 4, 4), 1.0, device="cuda")
+    ops.fc_wgrad(small.to(BF16), big.view(B, K), dw, beta=1.0)
+    assert rel_l2(dw - 1.0, refw) < 1e-4
+    dw0 = torch.full((Ns, C, 4, 4), 3.0, device="cuda")
+    ops.fc_wgrad(small.to(BF16).float(), big.view(B, K), dw0, beta=0.0)
+    assert rel_l2(dw0, refw) < 1e-4
+
+
+@pytest.mark.parametrize("P,C,act", [(64 * 16 * 16, 128, 1), (37, 256, 2), (8, 100, 1), (4 * 16, 2048, 2),
+                                      (2 * 128 * 128, 64, 2)])
+def test_bn_act_fwd_bwd(P, C, act):
+    ops = ops_mod()
+    z = (rnd(P, C, seed=1) * 1.5 + 0.3).to(BF16)
+    gamma = 1.0 + 0.2 * rnd(C, seed=2)
+    beta = 0.1 * rnd(C, seed=3)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    zr = z.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    pre = F.batch_norm(zr, rm_ref, rv_ref, gr, br, training=True, momentum=0.1, eps=1e-5)
+    ref = F.leaky_relu(pre, 0.2) if act == 1 else F.relu(pre)
+    stats = ops.bn_stats(z, gamma, beta, rm, rv)
+    y = ops.bn_act_fwd(z, stats, act)
+    assert torch.allclose(stats[0], zr.detach().mean(0), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(rm, rm_ref, atol=1e-6, rtol=1e-5) and torch.allclose(rv, rv_ref, atol=1e-6, rtol=1e-4)
+    assert rel_l2(y, ref) < 4e-3
+    dy = rnd(P, C, seed=4).to(BF16)
+    dy2 = rnd(P, C, seed=5).to(BF16)
+    rows = 4 if P % 4 == 0 else 1
+    bc = rnd(rows, C, seed=6)
+    coef = 0.37
+    g_total = dy.float() + dy2.float() + coef * bc.repeat(P // rows, 1)
+    # reference backward with the kernel's own activation signs (sign of the bf16 output)
+    slope = 0.2 if act == 1 else 0.0
+    mask = torch.where(y.float() > 0, 1.0, slope)
+    pre.backward(g_total * mask)
+    dgamma = torch.full((C,), 2.0, device="cuda")
+    dbeta = torch.full((C,), -1.0, device="cuda")
+    dz = ops.bn_act_bwd(dy, y, z, stats, gamma, act, 0.2, dgamma, dbeta, 1.0, dy2, bc.contiguous(), coef)
+    assert rel_l2(dgamma - 2.0, gr.grad) < 2e-3
+    assert rel_l2(dbeta + 1.0, br.grad) < 2e-3
+    assert rel_l2(dz, zr.grad) < 6e-3
+
+
+def test_bn_eval():
+    ops = ops_mod()
+    P, C = 50, 128
+    z = rnd(P, C, seed=1).to(BF16)
+    gamma, beta = 1 + 0.1 * rnd(C, seed=2), 0.1 * rnd(C, seed=3)
+    rm, rv = 0.2 * rnd(C, seed=4), 1 + 0.3 * torch.rand(C, device="cuda")
+    ref = F.relu(F.batch_norm(z.float(), rm, rv, gamma, beta, training=False, eps=1e-5))
+    y = ops.bn_act_fwd(z, ops.bn_eval_stats(gamma, beta, rm, rv), 2)
+    assert rel_l2(y, ref) < 4e-3
+
+
+def test_gan_bce():
+    ops = ops_mod()
+    B = 64
+    lr_ = rnd(B, seed=1) * 3
+    lf_ = rnd(B, seed=2) * 3
+    lf_[0], lf_[1], lr_[2] = -200.0, 200.0, -150.0        # saturated sigmoid: the -100 clamp and zero-gradient cases
+    a = lr_.clone().requires_grad_(True)
+    b = lf_.clone().requires_grad_(True)
+    bce = torch.nn.BCELoss()
+    pr, pf = torch.sigmoid(a).view(B, 1), torch.sigmoid(b).view(B, 1)
+    dis = 0.5 * (bce(pr, torch.ones_like(pr)) + bce(pf, torch.zeros_like(pf)))
+    gen = bce(pf, torch.ones_like(pf))
+    out = torch.zeros(2, device="cuda")
+    p_real, p_fake = ops.gan_bce_fwd(lr_, lf_, out)
+    assert torch.allclose(out, torch.stack([dis, gen]).detach(), rtol=1e-5, atol=1e-6)
+    (0.7 * dis + 0.3 * gen).backward()
+    dr, df = ops.gan_bce_bwd(p_real, p_fake, 0.7, 0.3)
+    assert torch.allclose(dr, a.grad, rtol=1e-4, atol=1e-7)
+    assert torch.allclose(df, b.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_mse_fm():
+    ops = ops_mod()
+    a, b = rnd(3, 3, 64, 64, seed=1), rnd(3, 3, 64, 64, seed=2)
+    out = torch.zeros(1, device="cuda")
+    ops.mse_fwd(a, b, out)
+    assert torch.allclose(out[0], F.mse_loss(a, b), rtol=1e-5)
+    ar = a.clone().requires_grad_(True)
+    (0.3 * F.mse_loss(ar, b)).backward()
+    da = ops.mse_bwd(a, b, 0.3)
+    assert torch.allclose(da, ar.grad, rtol=1e-5, atol=1e-9)
+    da2 = ops.mse_bwd(a, b, 0.3, da.clone(), accumulate=True)
+    assert torch.allclose(da2, 2 * ar.grad, rtol=1e-5, atol=1e-9)
+
+    Bn = 6
+    real = rnd(Bn, 8, 8, 128, seed=3).to(BF16)
+    fake = rnd(Bn, 8, 8, 128, seed=4).to(BF16)
+    fr = fake.float().requires_grad_(True)
+    d = real.float().mean(0) - fr.mean(0)
+    fm_ref = (d * d).mean()
+    out = torch.full((1,), 5.0, device="cuda")
+    diff = ops.fm_fwd(real, fake, out, accumulate=True)
+    assert torch.allclose(out[0] - 5.0, fm_ref.detach(), rtol=1e-4)
+    (0.9 * fm_ref).backward()
+    dfeat = ops.fm_bwd(diff, Bn, fake.shape, 0.9)
+    assert rel_l2(dfeat, fr.grad) < 4e-3
+
+
+def test_adam_matches_torch():
+    ops = ops_mod()
+    n = 10007
+    p = rnd(n, seed=1)
+    pt = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=2e-4, betas=(0.5, 0.999), weight_decay=1e-5)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 4):
+        g = rnd(n, seed=10 + step)
+        pt.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g * 4.0, m, v, 2e-4, 0.5, 0.999, 1e-8, 1e-5, step, grad_scale=0.25)
+        assert torch.allclose(p, pt.detach(), rtol=1e-5, atol=1e-7), step

@@ -1,0 +1,166 @@
+"""Module- and step-level parity on the GPU against the oracle (the reference restated in stock fp32 PyTorch,
+run here on the same device with TF32 disabled), identical seeded weights and synthetic batches.
+
+Tolerances follow SURVEY.md F9: bf16-operand kernels chained through the BatchNorm stack deviate a few percent
+on activations and up to tens of percent (rel-L2) on early-layer weight gradients, while losses agree to ~1e-3;
+so activations are held to 5e-2 rel-L2, gradients to cosine similarity >= 0.9 / rel-L2 <= 0.5, losses to
+5 % + 0.02 absolute."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def cos(a, b):
+    a, b = a.float().flatten(), b.float().flatten()
+    return float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def make_pair(kind, S, seed=1234):
+    import oracle
+    from discogan_modernized_b200 import model
+    torch.manual_seed(seed)
+    ref = (oracle.Generator(True, S) if kind == "G" else oracle.Discriminator(S)).cuda()
+    new = (model.Generator(True, S) if kind == "G" else model.Discriminator(S))
+    new.load_state_dict(ref.state_dict(), strict=True)          # state-dict compatibility is part of the boundary
+    return ref, new.cuda()
+
+
+@pytest.mark.parametrize("S,B", [(64, 4), (32, 3), (128, 2)])
+def test_discriminator_forward_backward(S, B):
+    ref, new = make_pair("D", S)
+    x = torch.rand(B, 3, S, S, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    xr = x.clone().requires_grad_(True)
+    xn = x.clone().requires_grad_(True)
+    pr, fr = ref(xr)
+    pn, fn_ = new(xn)
+    assert pn.shape == pr.shape == (B, 1, 1, 1) and pn.dtype == torch.float32
+    assert len(fn_) == len(fr) == ref.n_down - 1
+    assert torch.allclose(pn, pr, atol=3e-2)
+    for a, b in zip(fn_, fr):
+        assert a.shape == b.shape and a.dtype == torch.float32 and a.is_contiguous()
+        assert rel_l2(a, b) < 5e-2
+    # a loss touching the probability and every feature map
+    def loss(p, feats):
+        return p.log().mean() + sum((f.mean(0) ** 2).mean() for f in feats)
+    loss(pr, fr).backward()
+    loss(pn, fn_).backward()
+    assert cos(xn.grad, xr.grad) > 0.9
+    for (name, a), (_, b) in zip(new.named_parameters(), ref.named_parameters()):
+        assert a.grad is not None and a.grad.shape == b.grad.shape, name
+        assert cos(a.grad, b.grad) > 0.9, (name, cos(a.grad, b.grad))
+        assert rel_l2(a.grad, b.grad) < 0.5, (name, rel_l2(a.grad, b.grad))
+    for (name, a), (_, b) in zip(new.named_buffers(), ref.named_buffers()):
+        if a.dtype == torch.int64:
+            assert torch.equal(a, b), name
+        else:
+            assert torch.allclose(a, b, rtol=5e-2, atol=5e-3), name
+
+
+@pytest.mark.parametrize("S,B", [(64, 4), (32, 3), (128, 2)])
+def test_generator_forward_backward(S, B):
+    ref, new = make_pair("G", S)
+    x = torch.rand(B, 3, S, S, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6))
+    xr = x.clone().requires_grad_(True)
+    xn = x.clone().requires_grad_(True)
+    yr, yn = ref(xr), new(xn)
+    assert yn.shape == yr.shape and yn.dtype == torch.float32
+    assert rel_l2(yn, yr) < 5e-2
+    t = torch.rand_like(yr)
+    ((yr - t) ** 2).mean().backward()
+    ((yn - t) ** 2).mean().backward()
+    assert cos(xn.grad, xr.grad) > 0.85
+    bad = []
+    for (name, a), (_, b) in zip(new.named_parameters(), ref.named_parameters()):
+        assert a.grad is not None, name
+        c = cos(a.grad, b.grad)
+        if c < 0.85:
+            bad.append((name, c, rel_l2(a.grad, b.grad)))
+    assert not bad, bad
+
+
+def test_generator_eval_and_nograd():
+    ref, new = make_pair("G", 64)
+    x = torch.rand(5, 3, 64, 64, device="cuda")
+    with torch.no_grad():      # train-mode no_grad forwards update running stats (save_sample_images semantics)
+        ref(x); new(x)
+    ref.eval(); new.eval()
+    with torch.no_grad():
+        yr, yn = ref(x[:1]), new(x[:1])       # batch 1 is legal in eval mode (inference.py:168-172)
+    assert rel_l2(yn, yr) < 5e-2
+    assert int(new.encoder[3].num_batches_tracked) == 1
+
+
+def test_error_behaviour():
+    from discogan_modernized_b200 import model
+    D = model.Discriminator(64).cuda()
+    with pytest.raises(RuntimeError):
+        D(torch.rand(2, 3, 32, 32, device="cuda"))           # wrong spatial size
+    with pytest.raises(RuntimeError):
+        D(torch.rand(2, 3, 64, 64))                            # CPU tensor: no CPU path
+    with pytest.raises(ValueError):
+        model.Generator(image_size=64).cuda()(torch.rand(1, 3, 64, 64, device="cuda"))   # B=1 in training
+    with pytest.raises(ValueError):
+        model.Generator(image_size=48)
+
+
+@pytest.mark.parametrize("variant,arch", [("image_translation", "discogan"), ("angle_pairing", "discogan"),
+                                          ("image_translation", "recongan"), ("image_translation", "gan")])
+def test_train_step_matches_oracle(variant, arch):
+    from discogan_modernized_b200 import DiscoGANTrainer, model
+    from oracle.step import OracleStep, build_nets, synthetic_batch
+    S, B, steps = 64, 8, 6
+    ref_nets = build_nets(S, seed=1234, device="cuda")
+    torch.manual_seed(1234)
+    nets = [model.Generator(True, S), model.Generator(True, S), model.Discriminator(S), model.Discriminator(S)]
+    for n, r in zip(nets, ref_nets):
+        n.load_state_dict(r.state_dict())
+    tr = DiscoGANTrainer(image_size=S, nets=nets, model_arch=arch, variant=variant)
+    ref = OracleStep(ref_nets, model_arch=arch, variant=variant, device="cuda")
+    for it in range(steps):
+        A, Bt = synthetic_batch(B, S, step=it, device="cuda")
+        was_dis = tr.step(A, Bt)
+        want = ref.step(A, Bt)
+        assert was_dis == want["is_dis_step"]
+        got = tr.losses()
+        for k, v in got.items():
+            assert abs(v - want[k]) <= 0.05 * abs(want[k]) + 0.02, (it, k, v, want[k])
+    # parameters moved the same way: compare the update direction of a late and an early layer
+    for new, old, key in ((tr.D_A, ref_nets[2], "conv4.weight"), (tr.G_B, ref_nets[1], "decoder.0.weight")):
+        a, b = dict(new.named_parameters())[key], dict(old.named_parameters())[key]
+        if arch != "discogan" and new is tr.D_A:
+            continue
+        assert rel_l2(a, b) < 2e-2, (key, rel_l2(a, b))
+    if arch == "gan":   # G_A and D_A never receive a gradient: untouched by Adam (and by weight decay)
+        torch.manual_seed(1234)
+        fresh = model.Generator(True, S)
+        assert torch.equal(tr.G_A.encoder[0].weight.cpu(), fresh.encoder[0].weight)
+
+
+def test_golden_family64(golden_dir):
+    """The committed CPU golden (oracle at 64^2, B=8, 3 iterations) replayed on the kernels."""
+    from discogan_modernized_b200 import DiscoGANTrainer, model
+    from oracle.step import synthetic_batch
+    g = torch.load(golden_dir / "family64_step_image_translation_discogan.pt")
+    torch.manual_seed(1234)
+    nets = [model.Generator(True, 64), model.Generator(True, 64), model.Discriminator(64), model.Discriminator(64)]
+    tr = DiscoGANTrainer(image_size=64, nets=nets)
+    for it in range(3):
+        A, B = synthetic_batch(8, 64, step=it, device="cuda")
+        tr.step(A, B)
+        got = tr.losses()
+        for k, v in g["logs"][it].items():
+            if k in got:
+                assert abs(got[k] - v) <= 0.05 * abs(v) + 0.02, (it, k, got[k], v)
