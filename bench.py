@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- DiscoGAN train-step throughput (image-pairs/s) on B200, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--image-size 64] [--batch 64]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+A step is one iteration of the reference loop (image_translation.py:335-390) on one synthetic A/B batch pair:
+D step when iter % 3 == 0, else G step; K is rounded to whole D,G,G cycles.  `value` is whole-job image-pairs/s
+with the batches already resident in HBM; `e2e` is the same loop fed from pinned host buffers with the H2D copy of
+both batches and a D2H read of the eight losses inside the timed region every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--image-size", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 64 at 64^2, 32 at 512^2)")
+    ap.add_argument("--model-arch", default="discogan")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--also-512", type=int, default=1, help="also report a short 512^2 B=32 measurement at N=1")
+    return ap.parse_args()
+
+
+def workload_name(S, B):
+    names = {64: "celebA Male->Smiling discogan 64x64 (synthetic faces)", 512: "tops2hanbok discogan 512x512 (synthetic)"}
+    return f"{names.get(S, f'discogan {S}x{S}')} batch {B} per GPU, D:G:G schedule, Adam"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------
+# work accounting (SURVEY.md 8-A0 / BASELINE.md section 2)
+# ---------------------------------------------------------------------------------------------------
+def conv_flops(B, Hs, Cs, Cb):
+    return 2.0 * B * Hs * Hs * Cs * Cb * 16
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the restated reference step (oracle port) on the host CPU cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_pairs_per_s(S, B, steps, warmup, arch, budget_s=200.0):
+    import torch
+    from oracle.step import OracleStep, build_nets, synthetic_batch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    st = OracleStep(build_nets(S, seed=1234), model_arch=arch)
+    A, Bt = synthetic_batch(B, S, step=0)
+    t0 = time.perf_counter()
+    st.step(A, Bt)                                   # first (untimed) step, also calibrates the sample size
+    t1 = time.perf_counter() - t0
+    Bs = B
+    if t1 * (steps + warmup) > budget_s:              # bound the sample: shrink the per-step batch
+        Bs = max(2, int(B * budget_s / (t1 * (steps + warmup))))
+        Bs = min(B, max(2, Bs))
+    for i in range(max(0, warmup - 1)):
+        A, Bt = synthetic_batch(Bs, S, step=i + 1)
+        st.step(A, Bt)
+    batches = [synthetic_batch(Bs, S, step=100 + i) for i in range(min(steps, 3))]
+    t0 = time.perf_counter()
+    for i in range(steps):
+        A, Bt = batches[i % len(batches)]
+        st.step(A, Bt)
+    dt = time.perf_counter() - t0
+    sample = f"{steps} steps (D:G:G) of the oracle port at {S}x{S}, batch {Bs} per step, fp32, {cores} threads"
+    return Bs * steps / dt, dt / steps * 1e3, cores, sample, Bs
+
+
+def run_reference(args, S, B):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(3, args.steps // 3 * 3)
+    v, ms, cores, sample, Bs = cpu_reference_pairs_per_s(S, B, steps, max(1, args.warmup), args.model_arch)
+    line = {
+        "impl": "reference", "metric": "train image-pairs/sec", "value": v, "unit": "image-pairs/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(S, B), "image_size": S, "batch_per_gpu": B, "sample_batch": Bs,
+                   "model_arch": args.model_arch},
+        "cpu_baseline": {"value": v, "unit": "image-pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "image-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def timed_steps(tr, batches, steps, torch, dist, world):
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start.record()
+    for i in range(steps):
+        A, B = batches[i % len(batches)]
+        tr.step(A, B)
+    end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = start.elapsed_time(end)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return ms
+
+
+def timed_steps_e2e(tr, host_batches, steps, torch, dist, world):
+    """Public-API loop fed from pinned host memory: H2D of both batches and D2H of the 8 losses every step."""
+    dev_A = torch.empty_like(host_batches[0][0], device="cuda")
+    dev_B = torch.empty_like(host_batches[0][1], device="cuda")
+    host_loss = torch.empty(8, dtype=torch.float32).pin_memory()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start.record()
+    for i in range(steps):
+        hA, hB = host_batches[i % len(host_batches)]
+        dev_A.copy_(hA, non_blocking=True)
+        dev_B.copy_(hB, non_blocking=True)
+        tr.step(dev_A, dev_B)
+        host_loss.copy_(tr.loss_buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the losses each step
+    end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = start.elapsed_time(end)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    h2d = 2 * host_batches[0][0].numel() * 4
+    return ms, h2d, 32
+
+
+def measure_roofline(tr, batches, torch, pk):
+    """Per-launch CUDA-event timing of the tensor-core convolution kernels over one D,G,G cycle (separate from
+    the throughput region so the events do not perturb it)."""
+    from discogan_modernized_b200 import ops
+    recs = []
+    orig = {n: getattr(ops, n) for n in ("conv_down", "conv_up", "conv_wgrad")}
+
+    def wrap(name, fn):
+        def inner(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **k)
+            e.record()
+            if name == "conv_down":
+                big, wd = a[0], a[1]
+                fl = conv_flops(big.shape[0], big.shape[1] // 2, wd.shape[0], big.shape[3])
+            elif name == "conv_up":
+                small, wu = a[0], a[1]
+                fl = conv_flops(small.shape[0], small.shape[1], small.shape[3], wu.shape[0])
+            else:
+                small, big = a[0], a[1]
+                fl = conv_flops(small.shape[0], small.shape[1], small.shape[3], big.shape[3])
+            recs.append((name, fl, s, e))
+            return out
+        return inner
+
+    import discogan_modernized_b200.model as model
+    for n, f in orig.items():
+        setattr(ops, n, wrap(n, f))
+    try:
+        for i in range(3):
+            A, B = batches[i % len(batches)]
+            tr.step(A, B)
+        torch.cuda.synchronize()
+    finally:
+        for n, f in orig.items():
+            setattr(ops, n, f)
+    by = {}
+    for name, fl, s, e in recs:
+        d = by.setdefault(name, [0.0, 0.0, 0])
+        d[0] += fl
+        d[1] += s.elapsed_time(e) * 1e-3
+        d[2] += 1
+    out = {}
+    for name, (fl, sec, n) in by.items():
+        out[name] = {"launches": n, "tflops": fl / sec / 1e12 if sec > 0 else 0.0, "avg_us": sec / n * 1e6, "seconds": sec}
+    gemm_fl = sum(by[n][0] for n in ("conv_down", "conv_up") if n in by)
+    gemm_s = sum(by[n][1] for n in ("conv_down", "conv_up") if n in by)
+    gemm_n = sum(by[n][2] for n in ("conv_down", "conv_up") if n in by)
+    ach = gemm_fl / gemm_s / 1e12 if gemm_s > 0 else 0.0
+    roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: conv fprop/dgrad, convT fprop/dgrad)",
+            "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+            "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside the step)", "traffic": None,
+            "launches_per_cycle": gemm_n, "avg_launch_us": gemm_s / max(gemm_n, 1) * 1e6,
+            "algorithmic": "2*B*Ho*Wo*Co*Ci*16 FLOP per launch"}
+    return roof, out
+
+
+def run_b200(args, S, B):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from discogan_modernized_b200 import DiscoGANTrainer, _lib
+    from oracle.step import synthetic_batch           # seeded synthetic inputs only (no oracle compute on this arm)
+
+    steps = max(3, args.steps // 3 * 3)
+    warmup = max(3, args.warmup)
+    tr = DiscoGANTrainer(image_size=S, device=f"cuda:{local}", model_arch=args.model_arch, seed=1234)
+    host = [tuple(t.pin_memory() for t in synthetic_batch(B, S, step=i, rank=rank)) for i in range(3)]
+    batches = [(a.cuda(non_blocking=True), b.cuda(non_blocking=True)) for a, b in host]
+    for i in range(warmup):
+        tr.step(*batches[i % 3])
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L0 = _lib.lib().dg_launch_count()
+    ms = timed_steps(tr, batches, steps, torch, dist, world)
+    launches = _lib.lib().dg_launch_count() - L0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, h2d, d2h = timed_steps_e2e(tr, host, steps, torch, dist, world)
+    pairs = B * world * steps
+    value = pairs / (ms * 1e-3)
+    pk = peaks()
+    line = {
+        "metric": "train image-pairs/sec", "value": value, "unit": "image-pairs/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(S, B), "image_size": S, "batch_per_gpu": B, "global_batch": B * world,
+                   "model_arch": args.model_arch, "parallelism": f"dp{world}",
+                   "l2": "per-step working set (weights+grads+Adam moments+activations) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "image-pairs/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1:
+        if not args.no_roofline:
+            roof, per_kernel = measure_roofline(tr, batches, torch, pk)
+            line["roofline"] = roof
+            line["kernels"] = per_kernel
+        if args.also_512 and S != 512:
+            try:
+                del tr, batches
+                torch.cuda.empty_cache()
+                tr5 = DiscoGANTrainer(image_size=512, device=f"cuda:{local}", model_arch=args.model_arch, seed=1234)
+                b5 = [synthetic_batch(32, 512, step=i, device="cuda") for i in range(3)]
+                for i in range(3):
+                    tr5.step(*b5[i])
+                ms5 = timed_steps(tr5, b5, 6, torch, dist, 1)
+                roof5, per5 = (measure_roofline(tr5, b5, torch, pk) if not args.no_roofline else (None, None))
+                line["also"] = {"workload": workload_name(512, 32), "value": 32 * 6 / (ms5 * 1e-3), "unit": "image-pairs/s",
+                                "ms_per_step": ms5 / 6, "steps": 6, "roofline": roof5, "kernels": per5}
+                del tr5, b5
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                line["also"] = {"workload": workload_name(512, 32), "error": str(e)[:300]}
+        if not args.no_cpu_baseline:
+            v, msc, cores, sample, _ = cpu_reference_pairs_per_s(S, B, 3, 1, args.model_arch, budget_s=60.0)
+            line["cpu_baseline"] = {"value": v, "unit": "image-pairs/s", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    S = args.image_size
+    B = args.batch or (32 if S == 512 else 64)
+    if args.impl == "reference":
+        run_reference(args, S, B)
+    else:
+        run_b200(args, S, B)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,9 +31,10 @@ def parse_header(text=None):
     text = HEADER.read_text() if text is None else text
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     protos = {}
-    for m in re.finditer(r"(const char\*|int|size_t)\s+(dg_\w+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"(const char\*|int|size_t|long long)\s+(dg_\w+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.groups()
-        restype = {"int": ctypes.c_int, "size_t": ctypes.c_size_t, "const char*": ctypes.c_char_p}[ret]
+        restype = {"int": ctypes.c_int, "size_t": ctypes.c_size_t, "const char*": ctypes.c_char_p,
+                   "long long": ctypes.c_longlong}[ret]
         argtypes = []
         args = args.strip()
         if args and args != "void":

@@ -13,6 +13,7 @@ typedef __nv_bfloat16 bf16;
 #define DG_ERR_ARCH 3
 
 void dg_set_error(const char* fmt, ...);
+extern unsigned long long g_dg_launches;  // kernels launched through this library (bench.py's gpu_launches)
 
 #define DG_CHECK_ARG(cond, ...)                 \
   do {                                          \
@@ -24,6 +25,7 @@ void dg_set_error(const char* fmt, ...);
 
 #define DG_CHECK_LAUNCH(name)                                             \
   do {                                                                    \
+    ++g_dg_launches;                                                      \
     cudaError_t e__ = cudaGetLastError();                                 \
     if (e__ != cudaSuccess) {                                             \
       dg_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \

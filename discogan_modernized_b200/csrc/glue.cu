@@ -13,6 +13,7 @@
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
+unsigned long long g_dg_launches = 0;
 
 void dg_set_error(const char* fmt, ...) {
   va_list ap;
@@ -558,6 +559,7 @@ extern "C" {
 
 const char* dg_last_error(void) { return g_err; }
 int dg_version(void) { return 1; }
+long long dg_launch_count(void) { return (long long)g_dg_launches; }
 
 // Fails loudly unless the current device is a Blackwell sm_100 part with a loadable kernel image.
 int dg_device_check(void) {
@@ -579,9 +581,14 @@ int dg_device_check(void) {
 int dg_pack_weights(const float* w, void* wd, void* wu, int Cs, int Cb, cudaStream_t stream) {
   DG_CHECK_ARG(Cs > 0 && Cb > 0 && w, "pack_weights: bad args");
   const long long n = (long long)Cs * Cb;
-  if (wd) pack_wd_kernel<<<dg_ceil_div(n, 256), 256, 0, stream>>>(w, (bf16*)wd, Cs, Cb);
-  if (wu) pack_wu_kernel<<<dg_ceil_div(n, 256), 256, 0, stream>>>(w, (bf16*)wu, Cs, Cb);
-  DG_CHECK_LAUNCH("pack_weights");
+  if (wd) {
+    pack_wd_kernel<<<dg_ceil_div(n, 256), 256, 0, stream>>>(w, (bf16*)wd, Cs, Cb);
+    DG_CHECK_LAUNCH("pack_wd");
+  }
+  if (wu) {
+    pack_wu_kernel<<<dg_ceil_div(n, 256), 256, 0, stream>>>(w, (bf16*)wu, Cs, Cb);
+    DG_CHECK_LAUNCH("pack_wu");
+  }
   return DG_OK;
 }
 

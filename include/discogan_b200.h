@@ -30,6 +30,7 @@ enum { DG_ACT_NONE = 0, DG_ACT_LRELU = 1, DG_ACT_RELU = 2 };
 const char* dg_last_error(void);
 int dg_version(void);
 int dg_device_check(void); /* non-zero unless the current device is sm_100 */
+long long dg_launch_count(void); /* kernels launched through this library so far (process-wide) */
 
 /* ---- weights: fp32 W[Cs][Cb][4][4] -> bf16 Wd[Cs][16][Cb] (K-major for DOWN) and Wu[Cb][16][Cs] (for UP).
  * Either output may be NULL.  (Parameters: model.py:8-35,80-142.) */

@@ -1,0 +1,134 @@
+"""Host-side logic that needs no GPU: model structure / state-dict boundary, loss weights, flat buffers and the
+data-parallel reducer (gloo, world_size 2)."""
+import json
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from discogan_modernized_b200 import model
+from discogan_modernized_b200.train_step import FlatNet, GradReducer, loss_coefficients
+
+
+def test_state_dict_matches_reference(golden_dir):
+    s = json.loads((golden_dir / "ref512_structure.json").read_text())
+    with torch.device("meta"):
+        G = model.Generator(extra_layers=True)          # default image_size = 512, the reference topology
+        D = model.Discriminator()
+    assert {k: list(v.shape) for k, v in G.state_dict().items()} == s["generator"]
+    assert {k: list(v.shape) for k, v in D.state_dict().items()} == s["discriminator"]
+    assert [n for n, _ in G.named_parameters()] == s["generator_param_order"]
+    assert [n for n, _ in D.named_parameters()] == s["discriminator_param_order"]
+    assert G.main is None and hasattr(G, "encoder") and hasattr(G, "decoder")
+
+
+def test_default_init_equals_reference_init():
+    """Same RNG consumption as the reference constructors: seeding then constructing gives identical weights."""
+    for S in (64, 128):
+        torch.manual_seed(7); a = model.Generator(True, S); b = model.Discriminator(S)
+        torch.manual_seed(7); c = oracle.Generator(True, S); d = oracle.Discriminator(S)
+        for x, y in ((a, c), (b, d)):
+            for (k1, v1), (k2, v2) in zip(x.state_dict().items(), y.state_dict().items()):
+                assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_cpu_input_raises():
+    D = model.Discriminator(64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        D(torch.rand(2, 3, 64, 64))
+    with pytest.raises(ValueError):
+        model.family_channels(100)
+
+
+def test_loss_coefficients_match_autograd():
+    """d(gen_loss)/d(component) from image_translation.py:370-382 for every model_arch."""
+    for arch in ("discogan", "recongan", "gan"):
+        for rate in (0.01, 0.5, 0.9):
+            comp = {k: torch.tensor(float(i + 1), requires_grad=True) for i, k in
+                    enumerate(("gen_A", "fm_A", "gen_B", "fm_B", "recon_A", "recon_B"))}
+            gA = (comp["fm_B"] * 0.9 + comp["gen_B"] * 0.1) * (1 - rate) + comp["recon_A"] * rate
+            gB = (comp["fm_A"] * 0.9 + comp["gen_A"] * 0.1) * (1 - rate) + comp["recon_B"] * rate
+            loss = {"discogan": gA + gB, "recongan": gA, "gan": comp["gen_B"] * 0.1 + comp["fm_B"] * 0.9}[arch]
+            loss.backward()
+            co = loss_coefficients(arch, rate)
+            for k, v in comp.items():
+                want = 0.0 if v.grad is None else float(v.grad)
+                assert co[k] == pytest.approx(want, abs=1e-7), (arch, rate, k)
+    with pytest.raises(ValueError):
+        loss_coefficients("wgan", 0.5)
+
+
+def test_flatnet_views():
+    net = model.Discriminator(16)
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    fn = FlatNet(net)
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, before[k])
+    for p, o in zip(fn.params, fn.offsets):
+        assert p.data_ptr() == fn.flat_p.data_ptr() + 4 * o and o % 64 == 0
+        assert p.grad.data_ptr() == fn.flat_g.data_ptr() + 4 * o
+    fn.flat_g.fill_(1.0)
+    assert all(float(p.grad.sum()) == p.numel() for p in fn.params)
+    net.conv1.weight.grad = None
+    fn.zero_grad()
+    assert net.conv1.weight.grad is not None and float(fn.flat_g.abs().sum()) == 0.0
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                       # different weights per rank before the broadcast
+    net = model.Discriminator(16)
+    fn = FlatNet(net)
+    red = GradReducer()
+    assert red.enabled and red.world == world and red.grad_scale == 1.0 / world
+    red.broadcast_params([fn])
+    fn.flat_g.fill_(float(rank + 1))
+    red.launch(fn.flat_g)
+    red.join()
+    out[rank] = (fn.flat_p[:256].clone(), float(fn.flat_g[0]), float(fn.flat_g[-1]))
+    dist.destroy_process_group()
+
+
+def test_grad_reducer_gloo_world2():
+    world, port = 2, 29531
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
+        (p0, g0a, g0b), (p1, g1a, g1b) = out[0], out[1]
+    assert torch.equal(p0, p1)                          # rank 0's weights everywhere
+    assert g0a == g0b == g1a == g1b == 3.0              # summed; Adam applies grad_scale = 1/world
+
+
+def _dp_oracle_worker(rank, world, port, out):
+    """R-rank data parallel == each rank steps on its own shard with per-rank BN/FM and averaged gradients."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.step import OracleStep, build_nets, synthetic_batch
+    torch.set_num_threads(2)
+    st = OracleStep(build_nets(16))
+
+    def avg(nets):
+        for n in nets:
+            for p in n.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+                    p.grad /= world
+    for it in range(2):
+        A, B = synthetic_batch(4, 16, step=it, rank=rank)
+        st.step(A, B, grad_hook=avg)
+    out[rank] = (st.D_A.conv1.weight.detach().clone(), st.G_A.encoder[3].running_mean.clone())
+    dist.destroy_process_group()
+
+
+def test_dp_oracle_semantics_gloo_world2():
+    world, port = 2, 29532
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_dp_oracle_worker, args=(world, port, out), nprocs=world, join=True)
+        (w0, rm0), (w1, rm1) = out[0], out[1]
+    assert torch.allclose(w0, w1, atol=1e-7)            # weights stay synchronised
+    assert not torch.equal(rm0, rm1)                    # BatchNorm statistics stay per rank
