@@ -1,0 +1,153 @@
+"""Shared command-line plumbing for the re-hosted reference entry points.
+
+Flags and defaults follow the reference parsers (image_translation.py:21-81, angle_pairing.py:22-72,
+distributed_image_translation.py:48-126).  Data: the dataset pipeline (dataset.py) is outside
+the hot path this repo rebuilds, so batches are either synthetic (``--synthetic``, the default when the task's
+folders are absent; precedent batch_size_optimization.py:62-63) or read from two flat image folders
+(``--data_A DIR --data_B DIR``, resized to --image_size, scaled to [0,1], CHW).
+"""
+import argparse
+from datetime import datetime
+from pathlib import Path
+
+import torch
+
+from .train_step import DiscoGANTrainer
+
+
+def build_parser(kind):
+    angle = kind == "angle_pairing"
+    p = argparse.ArgumentParser(description=f"DiscoGAN ({kind}) on B200 kernels")
+    p.add_argument("--device", default="cuda")
+    p.add_argument("--task_name", default="car2car" if angle else "facescrub")
+    p.add_argument("--results_dir", default="./results/")
+    p.add_argument("--models_dir", default="./models/")
+    p.add_argument("--model_arch", default="discogan", choices=["discogan", "recongan", "gan"])
+    p.add_argument("--epochs", type=int, default=10 if angle else 100)
+    p.add_argument("--batch_size", type=int, default=64)
+    p.add_argument("--learning_rate", type=float, default=2e-4)
+    p.add_argument("--beta1", type=float, default=0.5)
+    p.add_argument("--beta2", type=float, default=0.999)
+    p.add_argument("--image_size", type=int, default=64)
+    p.add_argument("--gan_curriculum", type=int, default=10000)
+    p.add_argument("--starting_rate", type=float, default=0.9 if angle else 0.01)
+    p.add_argument("--default_rate", type=float, default=0.9 if angle else 0.5)
+    if not angle:
+        p.add_argument("--style_A", default=None)
+        p.add_argument("--style_B", default=None)
+        p.add_argument("--constraint", default=None)
+        p.add_argument("--constraint_type", default=None)
+    p.add_argument("--n_test", type=int, default=200)
+    p.add_argument("--update_interval", type=int, default=3)
+    p.add_argument("--log_interval", type=int, default=50)
+    p.add_argument("--image_save_interval", type=int, default=500 if angle else 1000)
+    p.add_argument("--model_save_interval", type=int, default=10000)
+    if kind == "distributed":
+        p.add_argument("--distributed", action="store_true")
+        p.add_argument("--local_rank", type=int, default=0)
+        p.add_argument("--world_size", type=int, default=4)
+        for n in ("gen_A", "gen_B", "dis_A", "dis_B"):
+            p.add_argument(f"--load_{n}", default=None)
+    # additions (not in the reference)
+    p.add_argument("--synthetic", action="store_true", help="uniform-random A/B batches")
+    p.add_argument("--data_A", default=None)
+    p.add_argument("--data_B", default=None)
+    p.add_argument("--iters_per_epoch", type=int, default=100, help="synthetic data only")
+    p.add_argument("--max_iters", type=int, default=None)
+    return p
+
+
+def load_folder(path, size):
+    from PIL import Image
+    import numpy as np
+    files = sorted(list(Path(path).glob("*.jpg")) + list(Path(path).glob("*.png")))
+    if not files:
+        raise FileNotFoundError(f"no .jpg/.png images under {path}")
+    out = []
+    for f in files:
+        im = Image.open(f).convert("RGB").resize((size, size))
+        out.append(torch.from_numpy(np.asarray(im).copy()).permute(2, 0, 1).float() / 255.0)
+    return torch.stack(out)
+
+
+class Batches:
+    """Per-epoch A/B batches; shuffles A and B independently like dataset.shuffle_data (dataset.py:24-35)."""
+
+    def __init__(self, args, rank=0, world=1):
+        self.bs, self.S, self.rank, self.world = args.batch_size, args.image_size, rank, world
+        if args.data_A and args.data_B and not args.synthetic:
+            self.A, self.B = load_folder(args.data_A, self.S), load_folder(args.data_B, self.S)
+            n = min(len(self.A), len(self.B)) // world
+            self.A, self.B = self.A[rank * n:(rank + 1) * n].pin_memory(), self.B[rank * n:(rank + 1) * n].pin_memory()
+            self.n_batches = n // self.bs
+        else:
+            self.A = self.B = None
+            self.n_batches = args.iters_per_epoch
+
+    def epoch(self, epoch):
+        g = torch.Generator().manual_seed(1000 * self.rank + epoch)
+        if self.A is None:
+            for _ in range(self.n_batches):
+                yield (torch.rand(self.bs, 3, self.S, self.S, generator=g).pin_memory(),
+                       torch.rand(self.bs, 3, self.S, self.S, generator=g).pin_memory())
+        else:
+            ia, ib = torch.randperm(len(self.A), generator=g), torch.randperm(len(self.B), generator=g)
+            for i in range(self.n_batches):
+                sl = slice(i * self.bs, (i + 1) * self.bs)
+                yield self.A[ia[sl]].pin_memory(), self.B[ib[sl]].pin_memory()
+
+
+def save_models(tr, model_path, tag):
+    """gen_A_{tag}.pth ... -- the reference's checkpoint names and state-dict layout (image_translation.py:420-432)."""
+    model_path.mkdir(parents=True, exist_ok=True)
+    for name, net in (("gen_A", tr.G_A), ("gen_B", tr.G_B), ("dis_A", tr.D_A), ("dis_B", tr.D_B)):
+        torch.save({k: v.detach().cpu().clone() for k, v in net.state_dict().items()}, model_path / f"{name}_{tag}.pth")
+
+
+def run_training(args, kind, rank=0, world=1, process_group=None):
+    variant = "angle_pairing" if kind == "angle_pairing" else "image_translation"
+    device = f"cuda:{rank}" if kind == "distributed" else ("cuda" if args.device == "cuda" else args.device)
+    ts = datetime.now().strftime("%Y%m%d_%H%M%S") + (f"_rank{rank}" if kind == "distributed" else "")
+    sub = Path(args.task_name) / (getattr(args, "style_A", None) or "") / args.model_arch / ts
+    result_path, model_path = Path(args.results_dir) / sub, Path(args.models_dir) / sub
+    if kind == "distributed":
+        torch.manual_seed(1234)                       # distributed_image_translation.py:372
+    tr = DiscoGANTrainer(image_size=args.image_size, device=device, model_arch=args.model_arch,
+                         learning_rate=args.learning_rate, beta1=args.beta1, beta2=args.beta2,
+                         update_interval=args.update_interval, gan_curriculum=args.gan_curriculum,
+                         starting_rate=args.starting_rate, default_rate=args.default_rate, variant=variant,
+                         process_group=process_group)
+    if kind == "distributed":
+        for flag, net in (("load_gen_A", tr.G_A), ("load_gen_B", tr.G_B), ("load_dis_A", tr.D_A), ("load_dis_B", tr.D_B)):
+            path = getattr(args, flag)
+            if path:
+                net.load_state_dict(torch.load(path, map_location=device))
+                net._packed.invalidate()
+    data = Batches(args, rank, world)
+    total = args.epochs * data.n_batches
+    log = None
+    if rank == 0:
+        result_path.mkdir(parents=True, exist_ok=True)
+        log = open(result_path / "training_log.txt", "w")
+        log.write(f"Training started at {ts}\nTask: {args.task_name}, Model: {args.model_arch}\n"
+                  f"Batch size: {args.batch_size}, Learning rate: {args.learning_rate}\n\n")
+    done = False
+    for epoch in range(args.epochs):
+        for A, B in data.epoch(epoch):
+            it = tr.iters
+            tr.step(A.to(device, non_blocking=True), B.to(device, non_blocking=True))
+            if rank == 0 and it % args.log_interval == 0:
+                line = tr.log_line(total)
+                print(line, flush=True)
+                log.write(line + "\n")
+            if rank == 0 and it % args.model_save_interval == 0 and it > 0:
+                save_models(tr, model_path, it)
+            if args.max_iters is not None and tr.iters >= args.max_iters:
+                done = True
+                break
+        if done:
+            break
+    if rank == 0:
+        save_models(tr, model_path, "final")
+        log.close()
+    return tr

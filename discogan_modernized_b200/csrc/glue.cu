@@ -517,20 +517,39 @@ fm_bwd_kernel(const float* __restrict__ diff, int B, long long n, float coef, bf
 // ------------------------------------------------------------------------------------------------
 // Adam (coupled L2 weight decay, torch.optim.Adam op order), flat fp32 buffers
 // ------------------------------------------------------------------------------------------------
+// state = {step count, 1 - beta1^step, sqrt(1 - beta2^step), unused}: kept on the device so a captured CUDA graph
+// of the train step advances the bias corrections on every replay.
+__global__ void adam_tick_kernel(float* __restrict__ state, float b1, float b2) {
+  const double step = (double)state[0] + 1.0;
+  state[0] = (float)step;
+  state[1] = (float)(1.0 - pow((double)b1, step));
+  state[2] = (float)sqrt(1.0 - pow((double)b2, step));
+}
+
 __global__ void __launch_bounds__(256)
-adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+            long long n4, float lr, float b1, float b2, float eps, float wd, const float* __restrict__ state,
             float grad_scale) {
-  const float step_size = lr / bc1;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float pi = p[i];
-    const float gi = g[i] * grad_scale + wd * pi;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;       // exp_avg.lerp_(grad, 1-beta1)
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+  const float step_size = lr / state[1];
+  const float bc2_sqrt = state[2];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pi = p[i], mi = m[i], vi = v[i];
+    const float4 gr = g[i];
+    float* pp = reinterpret_cast<float*>(&pi);
+    float* mp = reinterpret_cast<float*>(&mi);
+    float* vp = reinterpret_cast<float*>(&vi);
+    const float* gp = reinterpret_cast<const float*>(&gr);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gi = gp[k] * grad_scale + wd * pp[k];
+      mp[k] = b1 * mp[k] + (1.f - b1) * gi;        // exp_avg.lerp_(grad, 1-beta1)
+      vp[k] = b2 * vp[k] + (1.f - b2) * gi * gi;   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+      const float denom = sqrtf(vp[k]) / bc2_sqrt + eps;
+      pp[k] = pp[k] - step_size * (mp[k] / denom);
+    }
+    p[i] = pi;
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - step_size * (mi / denom);
   }
 }
 
@@ -766,14 +785,16 @@ int dg_fm_bwd(const float* diff, int B, long long n, float g, void* dfeat, cudaS
   return DG_OK;
 }
 
-// One Adam step over flat fp32 buffers; `step` is the 1-based step count of this parameter group.
+// One Adam step over flat fp32 buffers (n a multiple of 4, 16-byte aligned).  `state` is a device float[4]
+// {steps taken, bias corrections}; zero it once, every call advances it.
 int dg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                 float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream) {
-  DG_CHECK_ARG(n > 0 && p && g && m && v && step >= 1, "adam_step: bad args");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_kernel<<<ew_grid(n, sms()), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                                     (float)sqrt(bc2), grad_scale);
+                 float eps, float weight_decay, float* state, float grad_scale, cudaStream_t stream) {
+  DG_CHECK_ARG(n > 0 && n % 4 == 0 && p && g && m && v && state, "adam_step: bad args (n must be a multiple of 4)");
+  DG_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam_step: unaligned buffers");
+  adam_tick_kernel<<<1, 1, 0, stream>>>(state, beta1, beta2);
+  DG_CHECK_LAUNCH("adam_tick");
+  adam_kernel<<<ew_grid(n / 4, sms()), 256, 0, stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, lr,
+                                                         beta1, beta2, eps, weight_decay, state, grad_scale);
   DG_CHECK_LAUNCH("adam_step");
   return DG_OK;
 }

@@ -35,9 +35,9 @@ def family_channels(image_size: int):
 # packed bf16 weights, refreshed when the fp32 parameter changes
 # ---------------------------------------------------------------------------------------------
 class _PackedWeights:
-    """bf16 GEMM-layout copies of the fp32 conv weights, keyed by parameter; re-packed when the
-    parameter's version counter or storage changes.  Code that rewrites parameters behind autograd's
-    back (the fused Adam kernel) calls ``invalidate()``."""
+    """bf16 GEMM-layout copies of the fp32 conv weights, keyed by parameter; re-packed (in place, so captured CUDA
+    graphs keep valid pointers) when the parameter's version counter or storage changes.  Code that rewrites
+    parameters behind autograd's back (the fused Adam kernel) calls ``refresh()`` right after the update."""
 
     def __init__(self):
         self._cache = {}
@@ -46,11 +46,21 @@ class _PackedWeights:
         key = id(p)
         tag = (p._version, p.data_ptr())
         ent = self._cache.get(key)
-        if ent is None or ent[0] != tag:
+        if ent is None:
             wd, wu = ops.pack_weights(p.detach(), want_wd, want_wu)
-            ent = (tag, wd, wu)
+            ent = [tag, wd, wu, p]
             self._cache[key] = ent
+        elif ent[0] != tag:
+            ops.pack_weights(p.detach(), out=(ent[1], ent[2]))
+            ent[0] = tag
         return ent[1], ent[2]
+
+    def refresh(self):
+        """Re-pack every cached weight in place from the current fp32 values."""
+        for ent in self._cache.values():
+            p = ent[3]
+            ops.pack_weights(p.detach(), out=(ent[1], ent[2]))
+            ent[0] = (p._version, p.data_ptr())
 
     def invalidate(self):
         self._cache.clear()

@@ -29,15 +29,22 @@ def _ptr(t, dtype=None, name="tensor"):
 
 
 _scratch = {}
+scratch_generation = 0   # bumped whenever a scratch buffer is (re)allocated: captured CUDA graphs holding the old
+                         # pointer must be re-captured (train_step.DiscoGANTrainer checks this before every replay)
 
 
 def scratch(kind, nbytes, device):
     """Grow-only per-device scratch buffers (wgrad workspace, BN partials, reduction partials)."""
+    global scratch_generation
     key = (kind, device)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise KernelError(f"scratch buffer '{kind}' would be allocated during CUDA-graph capture; run one eager "
+                              "step first")
         buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
         _scratch[key] = buf
+        scratch_generation += 1
     return buf
 
 
@@ -46,11 +53,14 @@ def device_check():
 
 
 # ---- weights / layout ---------------------------------------------------------------------
-def pack_weights(w, want_wd=True, want_wu=True):
-    """fp32 [Cs,Cb,4,4] -> (bf16 Wd [Cs,16,Cb], bf16 Wu [Cb,16,Cs])."""
+def pack_weights(w, want_wd=True, want_wu=True, out=None):
+    """fp32 [Cs,Cb,4,4] -> (bf16 Wd [Cs,16,Cb], bf16 Wu [Cb,16,Cs]); `out=(wd, wu)` re-packs in place."""
     Cs, Cb = w.shape[0], w.shape[1]
-    wd = torch.empty(Cs, 16, Cb, dtype=BF16, device=w.device) if want_wd else None
-    wu = torch.empty(Cb, 16, Cs, dtype=BF16, device=w.device) if want_wu else None
+    if out is not None:
+        wd, wu = out
+    else:
+        wd = torch.empty(Cs, 16, Cb, dtype=BF16, device=w.device) if want_wd else None
+        wu = torch.empty(Cb, 16, Cs, dtype=BF16, device=w.device) if want_wu else None
     check(lib().dg_pack_weights(_ptr(w, F32, "w"), _ptr(wd), _ptr(wu), Cs, Cb, _stream()), "dg_pack_weights")
     return wd, wu
 
@@ -304,6 +314,8 @@ def fm_bwd(diff, B, shape, g):
 
 
 # ---- optimiser --------------------------------------------------------------------------------
-def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale=1.0):
+    """One torch.optim.Adam-equivalent step on flat buffers; `state` = device fp32[4] (zero-initialised once; holds
+    the step count and bias corrections so the call is CUDA-graph replayable)."""
     check(lib().dg_adam_step(_ptr(p, F32, "p"), _ptr(g, F32, "g"), _ptr(m, F32, "m"), _ptr(v, F32, "v"), p.numel(), lr, beta1,
-                             beta2, eps, weight_decay, step, grad_scale, _stream()), "dg_adam_step")
+                             beta2, eps, weight_decay, _ptr(state, F32, "state"), grad_scale, _stream()), "dg_adam_step")

@@ -15,8 +15,13 @@ as one hand-scheduled forward/backward over the kernel engines in ``model.py``:
   side stream as soon as that network's last backward pass has been enqueued (overlapping the
   remaining backward work); gradients are averaged over ranks, BatchNorm statistics stay per rank,
   the learning rate is not scaled (``distributed_image_translation.py:396-427`` semantics with the
-  ``broadcast_buffers`` crash of SURVEY.md F4 avoided).
+  ``broadcast_buffers`` crash of SURVEY.md F4 avoided);
+* the whole iteration (several hundred kernel launches, micro-seconds each at 64x64) is captured once
+  per (step kind, loss weights) into a CUDA graph and replayed: inputs are copied into static
+  buffers, the Adam step counter lives on the device.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -46,7 +51,7 @@ class FlatNet:
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.steps = 0
+        self.adam_state = torch.zeros(4, dtype=torch.float32, device=dev)   # {steps, 1-b1^t, sqrt(1-b2^t), -}
         for p, o in zip(params, offs):
             view = self.flat_p[o:o + p.numel()].view(p.shape)
             view.copy_(p.data)
@@ -62,10 +67,14 @@ class FlatNet:
                 p.grad = self.flat_g[o:o + p.numel()].view(p.shape)
 
     def adam(self, lr, beta1, beta2, eps, weight_decay, grad_scale):
-        self.steps += 1
+        """Adam over the flat buffers, then refresh the bf16 GEMM copies of the conv weights in place."""
         ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr, beta1, beta2, eps, weight_decay,
-                      self.steps, grad_scale)
-        self.net._packed.invalidate()
+                      self.adam_state, grad_scale)
+        self.net._packed.refresh()
+
+    @property
+    def steps(self):
+        return int(self.adam_state[0].item())
 
 
 class GradReducer:
@@ -134,13 +143,19 @@ class DiscoGANTrainer:
     """Owns G_A, G_B, D_A, D_B and performs reference-equivalent iterations with ``step(A, B)``.
 
     variant='angle_pairing' skips the first feature map in the FM loss and defaults both rates to 0.9
-    (``angle_pairing.py:55-57,115``)."""
+    (``angle_pairing.py:55-57,115``).  ``use_graphs``: replay captured CUDA graphs (default on; set
+    DISCOGAN_B200_GRAPHS=0 or pass False to launch every kernel eagerly)."""
 
     def __init__(self, image_size=512, device="cuda", model_arch="discogan", learning_rate=2e-4, beta1=0.5,
                  beta2=0.999, weight_decay=1e-5, update_interval=3, gan_curriculum=10000, starting_rate=None,
-                 default_rate=None, variant="image_translation", seed=None, nets=None, process_group=None):
-        ops.device_check()
+                 default_rate=None, variant="image_translation", seed=None, nets=None, process_group=None,
+                 use_graphs=None):
         self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DiscoGANTrainer runs on CUDA (sm_100a) only")
+        if self.device.index is not None:
+            torch.cuda.set_device(self.device)
+        ops.device_check()
         self.image_size = image_size
         self.model_arch = model_arch
         loss_coefficients(model_arch, 0.5)  # validates
@@ -161,6 +176,14 @@ class DiscoGANTrainer:
         self.reducer.broadcast_params(self.flat.values())
         self.loss_buf = torch.zeros(len(LOSS_NAMES), dtype=torch.float32, device=self.device)
         self.iters = 0
+        if use_graphs is None:
+            use_graphs = os.environ.get("DISCOGAN_B200_GRAPHS", "1") != "0"
+        self.use_graphs = use_graphs
+        self._graphs = {}        # (is_dis, rate, batch) -> CUDAGraph
+        self._eager_done = set()
+        self._static = {}        # batch -> (A, B) static input buffers
+        self._pool = None
+        self._scratch_gen = -1
 
     # ------------------------------------------------------------------------------------------
     def _disc_pair(self, D, real_img, fake_img, slot, save_real, save_fake):
@@ -187,6 +210,39 @@ class DiscoGANTrainer:
         discriminator step.  Losses of the iteration are in ``self.loss_buf`` (see ``losses()``)."""
         is_dis = self.iters % self.update_interval == 0
         rate = self.starting_rate if self.iters < self.gan_curriculum else self.default_rate
+        if not self.use_graphs:
+            self._step_impl(A, B, is_dis, rate)
+        else:
+            if self._scratch_gen != ops.scratch_generation and self._graphs:
+                self._graphs.clear()            # a scratch buffer moved: captured pointers are stale
+                self._eager_done.clear()
+            key = (is_dis, rate, A.shape[0])
+            g = self._graphs.get(key)
+            if g is None and key not in self._eager_done:
+                # first encounter: run eagerly (sizes scratch buffers, sets kernel attributes), capture next time
+                self._step_impl(A, B, is_dis, rate)
+                self._eager_done.add(key)
+            else:
+                st = self._static.get(A.shape[0])
+                if st is None:
+                    st = (torch.empty_like(A), torch.empty_like(B))
+                    self._static[A.shape[0]] = st
+                st[0].copy_(A, non_blocking=True)
+                st[1].copy_(B, non_blocking=True)
+                if g is None:
+                    g = torch.cuda.CUDAGraph()
+                    if self._pool is None:
+                        self._pool = torch.cuda.graph_pool_handle()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(g, pool=self._pool):
+                        self._step_impl(st[0], st[1], is_dis, rate)
+                    self._graphs[key] = g
+                    self._scratch_gen = ops.scratch_generation
+                g.replay()
+        self.iters += 1
+        return is_dis
+
+    def _step_impl(self, A, B, is_dis, rate):
         co = loss_coefficients(self.model_arch, rate)
         G_A, G_B, D_A, D_B = self.G_A, self.G_B, self.D_A, self.D_B
         save_g = not is_dis
@@ -215,12 +271,10 @@ class DiscoGANTrainer:
             use_a = co["gen_A"] != 0.0 or co["fm_A"] != 0.0      # losses through D_A(BA): reach G_A pass 1
             use_b = co["gen_B"] != 0.0 or co["fm_B"] != 0.0      # losses through D_B(AB): reach G_B pass 1
             stepped = []
-            if use_b or co["recon_A"] != 0.0:
+            if use_b or co["recon_A"] != 0.0 or co["recon_B"] != 0.0:
                 stepped.append(G_B)
             if use_a or co["recon_B"] != 0.0 or co["recon_A"] != 0.0:
                 stepped.append(G_A)
-            if co["recon_B"] != 0.0 and G_B not in stepped:
-                stepped.append(G_B)
             for G in stepped:
                 self.flat[G].zero_grad()
             # ---- everything that ends in G_B's first pass (input A): D_B(AB) and G_A(AB) -> ABA
@@ -250,8 +304,6 @@ class DiscoGANTrainer:
         red.join()
         for n in stepped:
             self.flat[n].adam(self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, red.grad_scale)
-        self.iters += 1
-        return is_dis
 
     def _disc_fake_backward(self, D, d, c_gen, c_fm, B):
         """Back-prop c_gen*gen_loss + c_fm*fm_loss through the fake pass of D down to its input image."""

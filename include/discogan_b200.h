@@ -110,8 +110,9 @@ int dg_fm_fwd(const void* real, const void* fake, int B, long long n, float* dif
 int dg_fm_bwd(const float* diff, int B, long long n, float g, void* dfeat, dg_stream_t stream);
 
 /* ---- optim.Adam(lr, betas, weight_decay=1e-5), image_translation.py:275-287 ---- */
+/* state: device float[4] {steps taken, 1-beta1^t, sqrt(1-beta2^t), -}; zero once, advanced by every call */
 int dg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                 float eps, float weight_decay, int step, float grad_scale, dg_stream_t stream);
+                 float eps, float weight_decay, float* state, float grad_scale, dg_stream_t stream);
 
 /* ---- debug-only SIMT versions of the tensor-core convolutions (never the product path) ---- */
 int dg_simt_conv4x4s2_fprop(const void* x, const void* wd, void* z, int B, int H, int W, int Cb, int Cs,

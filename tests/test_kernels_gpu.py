@@ -302,14 +302,16 @@ def test_mse_fm():
 
 def test_adam_matches_torch():
     ops = ops_mod()
-    n = 10007
+    n = 10008
     p = rnd(n, seed=1)
     pt = p.clone().requires_grad_(True)
     opt = torch.optim.Adam([pt], lr=2e-4, betas=(0.5, 0.999), weight_decay=1e-5)
     m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    state = torch.zeros(4, device="cuda")
     for step in range(1, 4):
         g = rnd(n, seed=10 + step)
         pt.grad = g.clone()
         opt.step()
-        ops.adam_step(p, g * 4.0, m, v, 2e-4, 0.5, 0.999, 1e-8, 1e-5, step, grad_scale=0.25)
+        ops.adam_step(p, g * 4.0, m, v, 2e-4, 0.5, 0.999, 1e-8, 1e-5, state, grad_scale=0.25)
         assert torch.allclose(p, pt.detach(), rtol=1e-5, atol=1e-7), step
+        assert int(state[0]) == step
