@@ -14,7 +14,7 @@ PKG_DIR = Path(__file__).resolve().parent
 ROOT = PKG_DIR.parent
 HEADER = ROOT / "include" / "discogan_b200.h"
 LIB_PATH = PKG_DIR / "libdiscogan_b200.so"
-SOURCES = [PKG_DIR / "csrc" / n for n in ("gemm_tc.cu", "glue.cu", "direct.cu")]
+SOURCES = [PKG_DIR / "csrc" / n for n in ("gemm_tc.cu", "c3_tc.cu", "glue.cu", "direct.cu")]
 
 _CTYPES = {
     "int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
     """Compile the CUDA sources for sm_100a into the in-tree shared library (nvcc cross-compiles
     without a GPU)."""
     if LIB_PATH.exists() and not force:
-        newest = max(p.stat().st_mtime for p in SOURCES + [PKG_DIR / "csrc" / "common.cuh"])
+        newest = max(p.stat().st_mtime for p in SOURCES + [PKG_DIR / "csrc" / "common.cuh", PKG_DIR / "csrc" / "tma_host.cuh"])
         if LIB_PATH.stat().st_mtime >= newest:
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")

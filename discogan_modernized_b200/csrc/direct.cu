@@ -290,7 +290,7 @@ fc_down_kernel(const bf16* __restrict__ big, const bf16* __restrict__ wd, TS* __
 
 // big[b][k] = sum_n small[b][n] * wd[n][k].  Thread = 8 consecutive k for 4 batch rows.
 template <typename TS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 fc_up_kernel(const TS* __restrict__ small, const bf16* __restrict__ wd, bf16* __restrict__ big, int B, int Ns, int K) {
   extern __shared__ float ssm[];  // [4][Ns]
   const int b0 = blockIdx.y * 4;
@@ -322,42 +322,34 @@ fc_up_kernel(const TS* __restrict__ small, const bf16* __restrict__ wd, bf16* __
 }
 
 // dw[n][c][tap] = beta*dw + sum_b small[b][n] * big[b][tap*C + c]   (PyTorch layout [Ns][C][4][4], fp32)
-// Thread = (n, 8 consecutive c): 16 taps x 8 channels of accumulators, 64-byte contiguous stores per channel.
+// Thread = (n, tap, 8 consecutive c): coalesced 16-byte loads of `big`, 2*C threads per n.
 template <typename TS>
 __global__ void __launch_bounds__(128)
 fc_wgrad_kernel(const TS* __restrict__ small, const bf16* __restrict__ big, float* __restrict__ dw, float beta, int B,
                 int Ns, int C) {
   const int n = blockIdx.y;
-  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (c0 >= C) return;
-  const int K = 16 * C;
-  float acc[16][8];
+  const int cv = C >> 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tap = idx / cv;
+  const int c0 = (idx - tap * cv) * 8;
+  if (tap >= 16) return;
+  const size_t K = (size_t)16 * C;
+  float acc[8];
 #pragma unroll
-  for (int t = 0; t < 16; ++t)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const bf16* bp = big + (size_t)tap * C + c0;
+#pragma unroll 4
   for (int b = 0; b < B; ++b) {
     const float s = ld_small<TS>(small + (size_t)b * Ns + n);
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(bp + (size_t)b * K), f);
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
-      float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(big + (size_t)b * K + (size_t)t * C + c0), f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[t][e] += s * f[e];
-    }
+    for (int e = 0; e < 8; ++e) acc[e] += s * f[e];
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    float* d = dw + ((size_t)n * C + c0 + e) * 16;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 o = make_float4(acc[4 * q][e], acc[4 * q + 1][e], acc[4 * q + 2][e], acc[4 * q + 3][e]);
-      if (beta != 0.f) {
-        const float4 old = *reinterpret_cast<float4*>(d + 4 * q);
-        o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
-      }
-      *reinterpret_cast<float4*>(d + 4 * q) = o;
-    }
+    float* d = dw + ((size_t)n * C + c0 + e) * 16 + tap;
+    *d = (beta != 0.f ? beta * *d : 0.f) + acc[e];
   }
 }
 
@@ -522,19 +514,19 @@ int dg_fc_down(const void* big, const void* wd, void* small, int small_f32, int 
 }
 int dg_fc_up(const void* small, int small_f32, const void* wd, void* big, int B, int Ns, int K, cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && Ns > 0 && K > 0 && K % 8 == 0, "fc_up: bad dims");
-  dim3 grid(dg_ceil_div(K / 8, 256), dg_ceil_div(B, 4));
+  dim3 grid(dg_ceil_div(K / 8, 128), dg_ceil_div(B, 4));
   const size_t smem = (size_t)4 * Ns * sizeof(float);
   if (small_f32)
-    fc_up_kernel<float><<<grid, 256, smem, stream>>>((const float*)small, (const bf16*)wd, (bf16*)big, B, Ns, K);
+    fc_up_kernel<float><<<grid, 128, smem, stream>>>((const float*)small, (const bf16*)wd, (bf16*)big, B, Ns, K);
   else
-    fc_up_kernel<bf16><<<grid, 256, smem, stream>>>((const bf16*)small, (const bf16*)wd, (bf16*)big, B, Ns, K);
+    fc_up_kernel<bf16><<<grid, 128, smem, stream>>>((const bf16*)small, (const bf16*)wd, (bf16*)big, B, Ns, K);
   DG_CHECK_LAUNCH("fc_up");
   return DG_OK;
 }
 int dg_fc_wgrad(const void* small, int small_f32, const void* big, float* dw, float beta, int B, int Ns, int C,
                 cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && Ns > 0 && C > 0 && C % 8 == 0 && Ns <= 65535, "fc_wgrad: bad dims");
-  dim3 grid(dg_ceil_div(C / 8, 128), Ns);
+  dim3 grid(dg_ceil_div(2 * C, 128), Ns);
   if (small_f32)
     fc_wgrad_kernel<float><<<grid, 128, 0, stream>>>((const float*)small, (const bf16*)big, dw, beta, B, Ns, C);
   else

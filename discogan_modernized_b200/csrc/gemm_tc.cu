@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tma_host.cuh"
 
 namespace {
 
@@ -45,6 +46,11 @@ struct ConvGemmParams {
   int num_tiles;
   int num_stages;
   bf16* out;
+  // optional epilogue extras
+  const bf16* mask;   // same shape as out: out *= (mask > 0 ? 1 : mask_slope)  (LeakyReLU derivative of a BN-less layer)
+  float mask_slope;
+  float* img;         // epilogue "image": 3 real output channels written as fp32 NCHW planes instead of `out`
+  int img_sigmoid, img_accumulate;
 };
 
 struct TileCoord {
@@ -192,24 +198,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         oy = 2 * (t.h0 + hl) + (t.par >> 1);
         ox = 2 * (t.w0 + wl) + (t.par & 1);
       }
-      bf16* orow = p.out + (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.N + (size_t)t.nt * p.block_n;
+      const size_t opix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
+      bf16* orow = p.out + opix * p.N + (size_t)t.nt * p.block_n;
       const bool valid = b < p.B;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
-      for (int c = 0; c < p.block_n; c += 32) {
+      if (p.img != nullptr) {
+        // 3-channel image epilogue (N padded to 16): fp32 NCHW planes, optional sigmoid / accumulate
         uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_32x32(taddr, r);   // columns >= 16 are never written by the MMA and are ignored
         tmem_ld_wait();
         if (valid) {
+          const size_t plane = (size_t)p.Ho * p.Wo;
+          float* o = p.img + (size_t)b * 3 * plane + (size_t)oy * p.Wo + ox;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
-            v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-            v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-            v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-            *reinterpret_cast<uint4*>(orow + c + 8 * j) = v;
+          for (int c = 0; c < 3; ++c) {
+            float v = __uint_as_float(r[c]);
+            if (p.img_sigmoid) v = 1.f / (1.f + expf(-v));
+            if (p.img_accumulate) v += o[c * plane];
+            o[c * plane] = v;
+          }
+        }
+      } else {
+        const bf16* mrow = p.mask ? p.mask + opix * p.N + (size_t)t.nt * p.block_n : nullptr;
+        for (int c = 0; c < p.block_n; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[8 * j + e]);
+              if (mrow) {
+                float m[8];
+                unpack8(*reinterpret_cast<const bf16x8*>(mrow + c + 8 * j), m);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] *= (m[e] > 0.f ? 1.f : p.mask_slope);
+              }
+              *reinterpret_cast<bf16x8*>(orow + c + 8 * j) = pack8(f);
+            }
           }
         }
       }
@@ -409,100 +439,24 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// host side
+// host side (tensor-map helpers live in tma_host.cuh)
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
-      dg_set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
-      return nullptr;
-    }
-    fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
-// bf16 tensor map, SWIZZLE_128B, zero fill out of bounds. dims/strides fastest-first; strides in elements.
-int make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides_elems,
-             const int* box) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return DG_ERR_CUDA;
-  cuuint64_t gdim[5], gstr[4];
-  cuuint32_t bdim[5], estr[5];
-  for (int i = 0; i < rank; ++i) {
-    gdim[i] = (cuuint64_t)dims[i];
-    bdim[i] = (cuuint32_t)box[i];
-    estr[i] = 1;
-    if (i > 0) gstr[i - 1] = (cuuint64_t)strides_elems[i] * 2;
-  }
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    dg_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %lld %lld %lld, box %d %d %d)", (int)r,
-                 rank, dims[0], dims[1], rank > 2 ? dims[2] : 0, box[0], box[1], rank > 2 ? box[2] : 0);
-    return DG_ERR_CUDA;
-  }
-  return DG_OK;
-}
-
-// parity-split view of an NHWC tensor [B,H,W,C]: dims {2C, W/2, 2, H/2, B}
-int make_parity_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h, int box_b) {
-  long long dims[5] = {2LL * C, W / 2, 2, H / 2, B};
-  long long str[5] = {1, 2LL * C, (long long)W * C, 2LL * W * C, (long long)H * W * C};
-  int box[5] = {64, box_w, 1, box_h, box_b};
-  return make_map(m, base, 5, dims, str, box);
-}
-// plain view of an NHWC tensor [B,H,W,C]: dims {C, W, H, B}
-int make_nhwc_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int box_w, int box_h, int box_b) {
-  long long dims[4] = {C, W, H, B};
-  long long str[4] = {1, C, (long long)W * C, (long long)H * W * C};
-  int box[4] = {64, box_w, box_h, box_b};
-  return make_map(m, base, 4, dims, str, box);
-}
-int make_weight_map(CUtensorMap* m, const void* base, int rows, int cols, int box_rows) {
-  long long dims[2] = {cols, rows};
-  long long str[2] = {1, cols};
-  int box[2] = {64, box_rows};
-  return make_map(m, base, 2, dims, str, box);
-}
-
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
-bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
-
-// split `pixels` = 128 or 32 over (W, H, B) of a power-of-two image
-void tile_shape(int pixels, int H, int W, int* Wt, int* Ht, int* Bt) {
-  *Wt = W < pixels ? W : pixels;
-  int rest = pixels / *Wt;
-  *Ht = H < rest ? H : rest;
-  *Bt = rest / *Ht;
-}
+struct ConvGemmExtras {
+  const void* mask = nullptr;
+  float mask_slope = 0.f;
+  float* img = nullptr;  // when set: Cb (mode 1 output channels) is the padded 16 and only 3 planes are written
+  int img_sigmoid = 0, img_accumulate = 0;
+};
 
 int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, int B, int Hs, int Ws, int Cs, int Cb,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, const ConvGemmExtras& ex = ConvGemmExtras()) {
   DG_CHECK_ARG(B > 0 && is_pow2(Hs) && is_pow2(Ws), "conv gemm: B=%d Hs=%d Ws=%d must be positive / powers of two", B,
                Hs, Ws);
-  DG_CHECK_ARG(Cs % 64 == 0 && Cb % 64 == 0 && Cs >= 64 && Cb >= 64, "conv gemm: Cs=%d Cb=%d must be multiples of 64",
-               Cs, Cb);
-  DG_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)wpacked & 15) == 0 && ((uintptr_t)out & 15) == 0,
+  const bool img_mode = ex.img != nullptr;
+  DG_CHECK_ARG(Cs % 64 == 0 && Cs >= 64 && ((Cb % 64 == 0 && Cb >= 64) || (img_mode && mode == 1 && Cb == 16)),
+               "conv gemm: Cs=%d Cb=%d must be multiples of 64", Cs, Cb);
+  DG_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)wpacked & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                   ((uintptr_t)ex.mask & 15) == 0,
                "conv gemm: pointers must be 16-byte aligned");
   ConvGemmParams p;
   p.mode = mode;
@@ -519,9 +473,9 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   p.cpk = p.Ck / 64;
   p.k_iters = (mode == 0 ? 16 : 4) * p.cpk;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b * (mode == 0 ? 1 : 4);
-  int bn = 64;
+  int bn = img_mode ? 16 : 64;
   const int cands[3] = {256, 128, 64};
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 3 && !img_mode; ++i) {
     if (N % cands[i]) continue;
     bn = cands[i];
     if ((long long)m_tiles * (N / bn) >= num_sms()) break;
@@ -532,6 +486,11 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   p.Ho = mode == 0 ? Hs : 2 * Hs;
   p.Wo = mode == 0 ? Ws : 2 * Ws;
   p.out = reinterpret_cast<bf16*>(out);
+  p.mask = reinterpret_cast<const bf16*>(ex.mask);
+  p.mask_slope = ex.mask_slope;
+  p.img = ex.img;
+  p.img_sigmoid = ex.img_sigmoid;
+  p.img_accumulate = ex.img_accumulate;
   const int stage_bytes = kATileBytes + bn * 128;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -580,7 +539,8 @@ void wgrad_plan(int B, int Hs, int Ws, int Cs, int Cb, WgradParams* p) {
   p->n_tiles = Cb / 64;
   const int work = p->m_tiles * p->n_tiles * 2;
   int splits = dg_ceil_div(2 * num_sms(), work);
-  if (splits > p->total_chunks) splits = p->total_chunks;
+  const int max_splits = p->total_chunks / 16;  // at least 16 K-chunks (512 pixels) per split: keeps the
+  if (splits > max_splits) splits = max_splits;  // workspace traffic below the operand traffic on small layers
   if (splits < 1) splits = 1;
   p->chunks_per_split = dg_ceil_div(p->total_chunks, splits);
   p->splits = dg_ceil_div(p->total_chunks, p->chunks_per_split);
@@ -599,6 +559,27 @@ int dg_conv4x4s2_fprop(const void* x, const void* wd, void* z, int B, int H, int
 int dg_conv4x4s2_dgrad(const void* dz, const void* wu, void* dx, int B, int Hs, int Ws, int Cs, int Cb,
                        cudaStream_t stream) {
   return launch_conv_gemm(1, dz, wu, dx, B, Hs, Ws, Cs, Cb, stream);
+}
+
+// dgrad whose consumer is a BN-less LeakyReLU layer: dx = dgrad * (mask > 0 ? 1 : slope), mask = that layer's output
+int dg_conv4x4s2_dgrad_masked(const void* dz, const void* wu, void* dx, const void* mask, float slope, int B, int Hs,
+                              int Ws, int Cs, int Cb, cudaStream_t stream) {
+  ConvGemmExtras ex;
+  ex.mask = mask;
+  ex.mask_slope = slope;
+  return launch_conv_gemm(1, dz, wu, dx, B, Hs, Ws, Cs, Cb, stream, ex);
+}
+
+// 64 -> 3 channel "up" layer on the tensor cores (N padded to 16): img[B,3,S,S] fp32 NCHW (+)= [sigmoid](convT(x64, wu3))
+// x64 = bf16 [B,S/2,S/2,64], wu3 = bf16 [16][16 taps][64] from dg_c3_pack_weights.
+int dg_c3_up_tc(const void* x64, const void* wu3, float* img, int B, int S, int sigmoid, int accumulate,
+                cudaStream_t stream) {
+  DG_CHECK_ARG(img != nullptr && S % 2 == 0, "c3_up_tc: bad args");
+  ConvGemmExtras ex;
+  ex.img = img;
+  ex.img_sigmoid = sigmoid;
+  ex.img_accumulate = accumulate;
+  return launch_conv_gemm(1, x64, wu3, nullptr, B, S / 2, S / 2, 64, 16, stream, ex);
 }
 
 size_t dg_conv4x4s2_wgrad_workspace(int B, int Hs, int Ws, int Cs, int Cb) {

@@ -200,12 +200,24 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ part_sum, con
                                          float* __restrict__ mean, float* __restrict__ invstd,
                                          float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ running_mean, float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  // block = 32 channels x 8 split lanes; partial rows are summed 8-way in parallel, then combined in smem
+  __shared__ double sh_s[8][32], sh_q[8][32];
+  const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double s = 0.0, q = 0.0;
-  for (int i = 0; i < splits; ++i) {
-    s += (double)part_sum[(size_t)i * C + c];
-    q += (double)part_sq[(size_t)i * C + c];
+  if (c < C)
+    for (int i = sy; i < splits; i += 8) {
+      s += (double)part_sum[(size_t)i * C + c];
+      q += (double)part_sq[(size_t)i * C + c];
+    }
+  sh_s[sy][cx] = s;
+  sh_q[sy][cx] = q;
+  __syncthreads();
+  if (sy != 0 || c >= C) return;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) {
+    s += sh_s[i][cx];
+    q += sh_q[i][cx];
   }
   const double m = s / (double)P;
   double var = q / (double)P - m * m;
@@ -316,12 +328,23 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part_g, const f
                                        long long P, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ invstd, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float beta_acc, float* __restrict__ coefs) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double sh_s[8][32], sh_q[8][32];
+  const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double sg = 0.0, sgx = 0.0;
-  for (int i = 0; i < splits; ++i) {
-    sg += (double)part_g[(size_t)i * C + c];
-    sgx += (double)part_gx[(size_t)i * C + c];
+  if (c < C)
+    for (int i = sy; i < splits; i += 8) {
+      sg += (double)part_g[(size_t)i * C + c];
+      sgx += (double)part_gx[(size_t)i * C + c];
+    }
+  sh_s[sy][cx] = sg;
+  sh_q[sy][cx] = sgx;
+  __syncthreads();
+  if (sy != 0 || c >= C) return;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) {
+    sg += sh_s[i][cx];
+    sgx += sh_q[i][cx];
   }
   if (dgamma) {
     dgamma[c] = (beta_acc != 0.f ? beta_acc * dgamma[c] : 0.f) + (float)sgx;
@@ -648,7 +671,7 @@ int dg_bn_stats(const void* z, long long P, int C, const float* gamma, const flo
   else
     bn_stats_partial_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq);
   DG_CHECK_LAUNCH("bn_stats_partial");
-  bn_stats_finalize_kernel<<<dg_ceil_div(C, 128), 128, 0, stream>>>(ps, pq, g.gy, P, C, eps, momentum, gamma, beta,
+  bn_stats_finalize_kernel<<<dg_ceil_div(C, 32), 256, 0, stream>>>(ps, pq, g.gy, P, C, eps, momentum, gamma, beta,
                                                                     stats, stats + C, stats + 2 * C, stats + 3 * C,
                                                                     running_mean, running_var);
   DG_CHECK_LAUNCH("bn_stats_finalize");
@@ -702,7 +725,7 @@ int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bca
                                                        (const bf16*)y, (const bf16*)z, mean, invstd, P, C, g.cw,
                                                        g.rows_iter, g.rows_split, act, slope, pg, pgx);
   DG_CHECK_LAUNCH("bn_bwd_partial");
-  bn_bwd_finalize_kernel<<<dg_ceil_div(C, 128), 128, 0, stream>>>(pg, pgx, g.gy, P, C, gamma, invstd, dgamma, dbeta,
+  bn_bwd_finalize_kernel<<<dg_ceil_div(C, 32), 256, 0, stream>>>(pg, pgx, g.gy, P, C, gamma, invstd, dgamma, dbeta,
                                                                   grad_beta, coefs);
   DG_CHECK_LAUNCH("bn_bwd_finalize");
   if (vec == 8)

@@ -43,15 +43,29 @@ class _PackedWeights:
         self._cache = {}
 
     def get(self, p, want_wd, want_wu):
+        """GEMM layers: (Wd [Cs,16,Cb], Wu [Cb,16,Cs])."""
+        return self._get(p, "gemm", want_wd, want_wu)
+
+    def get_c3(self, p):
+        """Image-side 3-channel layers: (wc [64,64], wu3 [16,16,64])."""
+        return self._get(p, "c3", True, True)
+
+    @staticmethod
+    def _pack(p, kind, want_a, want_b, out=None):
+        if kind == "c3":
+            return ops.c3_pack_weights(p.detach(), out=out)
+        return ops.pack_weights(p.detach(), want_a, want_b, out=out)
+
+    def _get(self, p, kind, want_a, want_b):
         key = id(p)
         tag = (p._version, p.data_ptr())
         ent = self._cache.get(key)
         if ent is None:
-            wd, wu = ops.pack_weights(p.detach(), want_wd, want_wu)
-            ent = [tag, wd, wu, p]
+            a, b = self._pack(p, kind, want_a, want_b)
+            ent = [tag, a, b, p, kind]
             self._cache[key] = ent
         elif ent[0] != tag:
-            ops.pack_weights(p.detach(), out=(ent[1], ent[2]))
+            self._pack(p, kind, True, True, out=(ent[1], ent[2]))
             ent[0] = tag
         return ent[1], ent[2]
 
@@ -59,7 +73,7 @@ class _PackedWeights:
         """Re-pack every cached weight in place from the current fp32 values."""
         for ent in self._cache.values():
             p = ent[3]
-            ops.pack_weights(p.detach(), out=(ent[1], ent[2]))
+            self._pack(p, ent[4], True, True, out=(ent[1], ent[2]))
             ent[0] = (p._version, p.data_ptr())
 
     def invalidate(self):
@@ -122,11 +136,21 @@ def _bn_act_bwd(dy, sv, bn, act, need_wgrad, dy2=None, bcast=None, bcast_coef=0.
     return dz.view(sv.z.shape)
 
 
+def _conv1_backward(pk, weight, ctx, dz1, need_dx, need_wgrad, dx_out, dx_accumulate):
+    """Backward of the image-side Conv2d(3,64,4,2,1)+LeakyReLU given dz1 = d(loss)/d(pre-activation)."""
+    if need_wgrad:
+        ops.c3_wgrad_tc(dz1, ctx.xp, _grad_buf(weight), 1.0)
+    if not need_dx:
+        return None
+    _, wu3 = pk.get_c3(weight)
+    return ops.c3_up_tc(dz1, wu3, sigmoid=False, out=dx_out, accumulate=dx_accumulate and dx_out is not None)
+
+
 # ---------------------------------------------------------------------------------------------
 # Discriminator
 # ---------------------------------------------------------------------------------------------
 class _DiscCtx:
-    __slots__ = ("x", "y1", "bn", "B")
+    __slots__ = ("xp", "y1", "bn", "B", "shape")
 
 
 def discriminator_forward(mod, x, save=True):
@@ -135,9 +159,11 @@ def discriminator_forward(mod, x, save=True):
     _check_input(x, mod.image_size, training)
     x = x.contiguous()
     pk = mod._packed
-    y = ops.conv_c3_in_fwd(x, mod.conv1.weight.detach(), LRELU_SLOPE)
+    xp = ops.img_pad_nhwc4(x)
+    wc, _ = pk.get_c3(mod.conv1.weight)
+    y = ops.c3_down_tc(xp, wc, ACT_LRELU, LRELU_SLOPE)
     ctx = _DiscCtx()
-    ctx.x, ctx.y1, ctx.bn, ctx.B = (x if save else None), y, [], x.shape[0]
+    ctx.xp, ctx.y1, ctx.bn, ctx.B, ctx.shape = (xp if save else None), y, [], x.shape[0], x.shape
     feats = []
     for k in range(2, mod.n_down + 1):
         conv, bn = getattr(mod, f"conv{k}"), getattr(mod, f"bn{k}")
@@ -176,14 +202,9 @@ def discriminator_backward(mod, ctx, dlogit, dfeats=None, fm_bcast=None, need_dx
         if need_wgrad:
             ops.conv_wgrad(dz, y_prev, _grad_buf(conv.weight), 1.0)
         _, wu = pk.get(conv.weight, True, True)
-        dy = ops.conv_up(dz, wu)
-    dx = None
-    if need_dx:
-        dx = dx_out if dx_out is not None else torch.empty_like(ctx.x)
-    if need_dx or need_wgrad:
-        ops.conv_c3_in_bwd(ctx.x, mod.conv1.weight.detach(), ctx.y1, dy, dx, dx_accumulate and dx_out is not None,
-                           _grad_buf(mod.conv1.weight) if need_wgrad else None, LRELU_SLOPE)
-    return dx
+        # the gradient reaching conv1's output also takes conv1's LeakyReLU derivative (fused in the epilogue)
+        dy = ops.conv_up(dz, wu, mask=ctx.y1 if i == 0 else None, slope=LRELU_SLOPE)
+    return _conv1_backward(pk, mod.conv1.weight, ctx, dy, need_dx, need_wgrad, dx_out, dx_accumulate)
 
 
 class _DiscFn(torch.autograd.Function):
@@ -258,7 +279,7 @@ class Discriminator(nn.Module):
 # Generator
 # ---------------------------------------------------------------------------------------------
 class _GenCtx:
-    __slots__ = ("x", "y1", "enc", "head", "dec0", "dec", "out", "B")
+    __slots__ = ("xp", "y1", "enc", "head", "dec0", "dec", "out", "B", "shape")
 
 
 def _gen_layers(mod):
@@ -281,8 +302,10 @@ def generator_forward(mod, x, save=True):
     pk = mod._packed
     enc_convs, enc_bns, head_conv, head_bn, dec_convs, dec_bns = _gen_layers(mod)
     ctx = _GenCtx()
-    ctx.B, ctx.x = B, (x if save else None)
-    y = ops.conv_c3_in_fwd(x, enc_convs[0].weight.detach(), LRELU_SLOPE)
+    xp = ops.img_pad_nhwc4(x)
+    ctx.B, ctx.xp, ctx.shape = B, (xp if save else None), x.shape
+    wc, _ = pk.get_c3(enc_convs[0].weight)
+    y = ops.c3_down_tc(xp, wc, ACT_LRELU, LRELU_SLOPE)
     ctx.y1, ctx.enc = y, []
     for conv, bn in zip(enc_convs[1:], enc_bns[1:]):
         wd, _ = pk.get(conv.weight, True, True)
@@ -306,7 +329,8 @@ def generator_forward(mod, x, save=True):
         z = ops.conv_up(y, wu)
         y, stats = _bn_act(z, bn, ACT_RELU, training)
         ctx.dec.append(_BnSave(z if save else None, y, stats))
-    out = ops.convT_c3_out_fwd(y, dec_convs[-1].weight.detach())
+    _, wu3 = pk.get_c3(dec_convs[-1].weight)
+    out = ops.c3_up_tc(y, wu3, sigmoid=True)
     ctx.out = out
     return out, ctx
 
@@ -318,8 +342,11 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
     enc_convs, enc_bns, head_conv, head_bn, dec_convs, dec_bns = _gen_layers(mod)
     dec_in = [ctx.dec0] + ctx.dec          # dec_in[j].y is the input of dec_convs[j+1]
     last = dec_convs[-1]
-    dy = ops.convT_c3_out_bwd(dec_in[-1].y, last.weight.detach(), ctx.out, dout.contiguous(), True,
-                              _grad_buf(last.weight) if need_wgrad else None)
+    dpre = ops.img_pad_nhwc4(dout.contiguous(), yimg=ctx.out)      # d(loss)/d(pre-sigmoid), padded NHWC4 bf16
+    if need_wgrad:
+        ops.c3_wgrad_tc(dec_in[-1].y, dpre, _grad_buf(last.weight), 1.0)
+    wc_last, _ = pk.get_c3(last.weight)
+    dy = ops.c3_down_tc(dpre, wc_last, ops.ACT_NONE)
     for j in range(len(ctx.dec), 0, -1):
         conv, bn = dec_convs[j], dec_bns[j]
         sv = ctx.dec[j - 1]
@@ -350,14 +377,8 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
         if need_wgrad:
             ops.conv_wgrad(dz, y_prev, _grad_buf(conv.weight), 1.0)
         _, wu = pk.get(conv.weight, True, True)
-        dy = ops.conv_up(dz, wu)
-    dx = None
-    if need_dx:
-        dx = dx_out if dx_out is not None else torch.empty_like(ctx.x)
-    if need_dx or need_wgrad:
-        ops.conv_c3_in_bwd(ctx.x, enc_convs[0].weight.detach(), ctx.y1, dy, dx, dx_accumulate and dx_out is not None,
-                           _grad_buf(enc_convs[0].weight) if need_wgrad else None, LRELU_SLOPE)
-    return dx
+        dy = ops.conv_up(dz, wu, mask=ctx.y1 if i == 1 else None, slope=LRELU_SLOPE)
+    return _conv1_backward(pk, enc_convs[0].weight, ctx, dy, need_dx, need_wgrad, dx_out, dx_accumulate)
 
 
 class _GenFn(torch.autograd.Function):

@@ -100,14 +100,22 @@ def conv_down(big, wd):
     return out
 
 
-def conv_up(small, wu):
-    """[B,Hs,Ws,Cs] x Wu[Cb,16,Cs] -> [B,2Hs,2Ws,Cb]  (Conv2d dgrad / ConvTranspose2d 4x4 s2 p1 forward)."""
+def conv_up(small, wu, mask=None, slope=0.2):
+    """[B,Hs,Ws,Cs] x Wu[Cb,16,Cs] -> [B,2Hs,2Ws,Cb]  (Conv2d dgrad / ConvTranspose2d 4x4 s2 p1 forward).
+    mask (bf16, output shape): multiply by the LeakyReLU derivative (mask > 0 ? 1 : slope) in the epilogue."""
     B, Hs, Ws, Cs = small.shape
     Cb = wu.shape[0]
     out = torch.empty(B, 2 * Hs, 2 * Ws, Cb, dtype=BF16, device=small.device)
+    if _conv_impl == "tc" and mask is not None:
+        check(lib().dg_conv4x4s2_dgrad_masked(_ptr(small, BF16, "small"), _ptr(wu, BF16, "wu"), _ptr(out),
+                                              _ptr(mask, BF16, "mask"), slope, B, Hs, Ws, Cs, Cb, _stream()),
+              "dg_conv4x4s2_dgrad_masked")
+        return out
     fn = lib().dg_conv4x4s2_dgrad if _conv_impl == "tc" else lib().dg_simt_conv4x4s2_dgrad
     check(fn(_ptr(small, BF16, "small"), _ptr(wu, BF16, "wu"), _ptr(out), B, Hs, Ws, Cs, Cb, _stream()),
           "dg_conv4x4s2_dgrad")
+    if mask is not None:   # simt debug path: apply the mask with stock ops
+        out = torch.where(mask > 0, out, out * slope)
     return out
 
 
@@ -129,7 +137,58 @@ def conv_wgrad(small, big, dw, beta=1.0):
                                    Ws, Cs, Cb, ws.data_ptr(), ws.numel(), _stream()), "dg_conv4x4s2_wgrad")
 
 
-# ---- image-side 3-channel layers ---------------------------------------------------------------
+# ---- image-side 3-channel layers, tensor-core path -----------------------------------------------
+def c3_pack_weights(w, out=None):
+    """fp32 [64,3,4,4] -> (wc bf16 [64,64] for the down GEMM, wu3 bf16 [16,16,64] for the up GEMM)."""
+    if out is not None:
+        wc, wu3 = out
+    else:
+        wc = torch.empty(64, 64, dtype=BF16, device=w.device)
+        wu3 = torch.empty(16, 16, 64, dtype=BF16, device=w.device)
+    check(lib().dg_c3_pack_weights(_ptr(w, F32, "w"), _ptr(wc), _ptr(wu3), _stream()), "dg_c3_pack_weights")
+    return wc, wu3
+
+
+def img_pad_nhwc4(img, yimg=None):
+    """fp32 NCHW [B,3,S,S] (times yimg*(1-yimg) if given) -> zero-padded bf16 NHWC4 [B,S+2,S+2,4]."""
+    B, _, S, _ = img.shape
+    out = torch.empty(B, S + 2, S + 2, 4, dtype=BF16, device=img.device)
+    check(lib().dg_img_pad_nhwc4(_ptr(img, F32, "img"), _ptr(yimg, F32, "yimg"), _ptr(out), B, S, _stream()),
+          "dg_img_pad_nhwc4")
+    return out
+
+
+def c3_down_tc(xp, wc, act, slope=0.2):
+    """padded NHWC4 image -> bf16 [B,S/2,S/2,64] = act(conv 4x4 s2 p1)."""
+    B, S = xp.shape[0], xp.shape[1] - 2
+    y = torch.empty(B, S // 2, S // 2, 64, dtype=BF16, device=xp.device)
+    check(lib().dg_c3_down_tc(_ptr(xp, BF16, "xp"), _ptr(wc, BF16, "wc"), _ptr(y), B, S, act, slope, _stream()),
+          "dg_c3_down_tc")
+    return y
+
+
+def c3_up_tc(x64, wu3, sigmoid, out=None, accumulate=False):
+    """bf16 [B,S/2,S/2,64] -> fp32 NCHW [B,3,S,S] (+)= [sigmoid](convT 4x4 s2 p1)."""
+    B, Hs = x64.shape[0], x64.shape[1]
+    S = 2 * Hs
+    if out is None:
+        out = torch.empty(B, 3, S, S, dtype=F32, device=x64.device)
+        accumulate = False
+    check(lib().dg_c3_up_tc(_ptr(x64, BF16, "x64"), _ptr(wu3, BF16, "wu3"), _ptr(out, F32, "img"), B, S, int(sigmoid),
+                            int(accumulate), _stream()), "dg_c3_up_tc")
+    return out
+
+
+def c3_wgrad_tc(v64, xp, dw, beta=1.0):
+    """dw[64,3,4,4] = beta*dw + sum_pixels v64 (x) patches(xp)."""
+    B, S = xp.shape[0], xp.shape[1] - 2
+    need = lib().dg_c3_wgrad_workspace(B, S)
+    ws = scratch("c3wgrad", need, v64.device)
+    check(lib().dg_c3_wgrad_tc(_ptr(v64, BF16, "v64"), _ptr(xp, BF16, "xp"), _ptr(dw, F32, "dw"), beta, B, S,
+                               ws.data_ptr(), ws.numel(), _stream()), "dg_c3_wgrad_tc")
+
+
+# ---- image-side 3-channel layers, direct SIMT kernels (debug reference) ---------------------------
 def conv_c3_in_fwd(x, w, slope=0.2):
     B, _, S, _ = x.shape
     y = torch.empty(B, S // 2, S // 2, 64, dtype=BF16, device=x.device)

@@ -47,6 +47,9 @@ int dg_conv4x4s2_fprop(const void* x_big, const void* wd, void* z_small, int B, 
 /* its data gradient (cuDNN bwd-data); also nn.ConvTranspose2d(ci,co,4,2,1) forward, model.py:118-138 */
 int dg_conv4x4s2_dgrad(const void* dz_small, const void* wu, void* dx_big, int B, int Hs, int Ws, int Cs, int Cb,
                        dg_stream_t stream);
+/* same, fused with the LeakyReLU derivative of the (BN-less) layer that produced x: dx *= (mask>0 ? 1 : slope) */
+int dg_conv4x4s2_dgrad_masked(const void* dz_small, const void* wu, void* dx_big, const void* mask, float slope, int B,
+                              int Hs, int Ws, int Cs, int Cb, dg_stream_t stream);
 /* weight gradient (cuDNN bwd-filter): dw[Cs][Cb][4][4] = beta*dw + sum small (x) big; needs a workspace */
 size_t dg_conv4x4s2_wgrad_workspace(int B, int Hs, int Ws, int Cs, int Cb);
 int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
@@ -68,6 +71,18 @@ int dg_conv_c3_in_bwd(const float* x, const float* w, const void* y, const void*
 int dg_convT_c3_out_fwd(const void* x, const float* w, float* y, int B, int S, dg_stream_t stream);
 int dg_convT_c3_out_bwd(const void* x, const float* w, const float* y, const float* dy, void* dx, float* dw, int B,
                         int S, dg_stream_t stream);
+
+/* tensor-core path of the same two layers: the image is first repacked (once per use) into a zero-padded NHWC4 bf16
+ * image [B,S+2,S+2,4] (optionally multiplied by y(1-y), the Sigmoid derivative); weights: wc bf16 [64][64],
+ * wu3 bf16 [16][16][64] from dg_c3_pack_weights */
+int dg_c3_pack_weights(const float* w, void* wc, void* wu3, dg_stream_t stream);
+int dg_img_pad_nhwc4(const float* img, const float* yimg, void* out, int B, int S, dg_stream_t stream);
+int dg_c3_down_tc(const void* xp, const void* wc, void* y, int B, int S, int act, float slope, dg_stream_t stream);
+int dg_c3_up_tc(const void* x64, const void* wu3, float* img, int B, int S, int sigmoid, int accumulate,
+                dg_stream_t stream);
+size_t dg_c3_wgrad_workspace(int B, int S);
+int dg_c3_wgrad_tc(const void* v64, const void* xp, float* dw, float beta, int B, int S, void* ws, size_t ws_bytes,
+                   dg_stream_t stream);
 
 /* ---- 4x4 "valid" heads as skinny products against Wd[Ns][K=16*C] ----
  * nn.Conv2d(C,100,4,1,0) model.py:107, nn.Conv2d(C,1,4,1,0) model.py:35: small = big . Wd^T          (fc_down)

@@ -315,3 +315,59 @@ def test_adam_matches_torch():
         ops.adam_step(p, g * 4.0, m, v, 2e-4, 0.5, 0.999, 1e-8, 1e-5, state, grad_scale=0.25)
         assert torch.allclose(p, pt.detach(), rtol=1e-5, atol=1e-7), step
         assert int(state[0]) == step
+
+
+# ---- tensor-core path of the image-side 3-channel layers ---------------------------------------------------
+@pytest.mark.parametrize("B,S", [(2, 16), (3, 64), (5, 8), (1, 256)])
+def test_c3_tc_down_up_wgrad(B, S):
+    ops = ops_mod()
+    gen = torch.Generator(device="cuda").manual_seed(S)
+    x = torch.rand(B, 3, S, S, device="cuda", generator=gen)
+    w = rnd(64, 3, 4, 4, seed=2, scale=0.2)
+    wc, wu3 = ops.c3_pack_weights(w)
+    wq = w.to(BF16).float()
+    xq = x.to(BF16).float()
+    # padded NHWC4 repack
+    xp = ops.img_pad_nhwc4(x)
+    assert xp.shape == (B, S + 2, S + 2, 4)
+    assert torch.equal(xp[:, 1:-1, 1:-1, :3].float(), xq.permute(0, 2, 3, 1))
+    assert float(xp[:, 0].abs().sum() + xp[:, -1].abs().sum() + xp[:, :, 0].abs().sum() + xp[:, :, -1].abs().sum()
+                 + xp[..., 3].abs().sum()) == 0.0
+    # down: conv1 forward
+    ref = F.leaky_relu(F.conv2d(xq, wq, stride=2, padding=1), 0.2)
+    y = ops.c3_down_tc(xp, wc, 1, 0.2)
+    assert rel_l2(to_nchw_f32(y), ref) < 4e-3
+    # down with the sigmoid derivative folded into the repack (dgrad of the last ConvTranspose2d)
+    yimg = torch.rand(B, 3, S, S, device="cuda", generator=gen)
+    dpre = (x * yimg * (1 - yimg)).to(BF16).float()
+    dp = ops.img_pad_nhwc4(x, yimg)
+    ref2 = F.conv2d(dpre, wq, stride=2, padding=1)
+    assert rel_l2(to_nchw_f32(ops.c3_down_tc(dp, wc, 0)), ref2) < 4e-3
+    # up: last ConvTranspose2d forward (+sigmoid) and accumulate mode
+    s64 = rnd(B, 64, S // 2, S // 2, seed=3).to(BF16)
+    refu = F.conv_transpose2d(s64.float(), wq, stride=2, padding=1)
+    img = ops.c3_up_tc(to_nhwc_bf16(s64.float()), wu3, sigmoid=True)
+    assert torch.allclose(img, torch.sigmoid(refu), atol=2e-5, rtol=1e-4)
+    acc = torch.full_like(img, 0.25)
+    ops.c3_up_tc(to_nhwc_bf16(s64.float()), wu3, sigmoid=False, out=acc, accumulate=True)
+    assert rel_l2(acc - 0.25, refu) < 1e-4
+    # wgrad
+    refw = torch.nn.grad.conv2d_weight(xq, (64, 3, 4, 4), s64.float(), stride=2, padding=1)
+    dw = torch.full((64, 3, 4, 4), 0.5, device="cuda")
+    ops.c3_wgrad_tc(to_nhwc_bf16(s64.float()), xp, dw, beta=1.0)
+    assert rel_l2(dw - 0.5, refw) < 1e-3
+    dw0 = torch.full((64, 3, 4, 4), 9.0, device="cuda")
+    ops.c3_wgrad_tc(to_nhwc_bf16(s64.float()), xp, dw0, beta=0.0)
+    assert rel_l2(dw0, refw) < 1e-3
+
+
+def test_conv_up_masked():
+    ops = ops_mod()
+    B, Hs, Cs, Cb = 3, 8, 128, 64
+    s = rnd(B, Cs, Hs, Hs, seed=3).to(BF16)
+    w = (rnd(Cs, Cb, 4, 4, seed=4) / (2 * Cs ** 0.5)).to(BF16).float()
+    mask = rnd(B, 2 * Hs, 2 * Hs, Cb, seed=5).to(BF16)
+    ref = F.conv_transpose2d(s.float(), w, stride=2, padding=1) * torch.where(to_nchw_f32(mask) > 0, 1.0, 0.2)
+    _, wu = ops.pack_weights(w)
+    out = ops.conv_up(to_nhwc_bf16(s.float()), wu, mask=mask, slope=0.2)
+    assert rel_l2(to_nchw_f32(out), ref) < 4e-3
