@@ -234,15 +234,17 @@ def measure_roofline(tr, batches, torch, pk):
             return out
         return inner
 
-    import discogan_modernized_b200.model as model
     for n, f in orig.items():
         setattr(ops, n, wrap(n, f))
+    saved_graphs = tr.use_graphs
+    tr.use_graphs = False                      # per-launch events need eager launches
     try:
         for i in range(3):
             A, B = batches[i % len(batches)]
             tr.step(A, B)
         torch.cuda.synchronize()
     finally:
+        tr.use_graphs = saved_graphs
         for n, f in orig.items():
             setattr(ops, n, f)
     by = {}
@@ -293,9 +295,9 @@ def run_b200(args, S, B):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    L0 = _lib.lib().dg_launch_count()
+    L0 = tr.kernel_launches
     ms = timed_steps(tr, batches, steps, torch, dist, world)
-    launches = _lib.lib().dg_launch_count() - L0
+    launches = tr.kernel_launches - L0          # kernels of libdiscogan_b200.so (eager launches + graph-replayed nodes)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, h2d, d2h = timed_steps_e2e(tr, host, steps, torch, dist, world)
     pairs = B * world * steps
@@ -306,7 +308,7 @@ def run_b200(args, S, B):
         "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(S, B), "image_size": S, "batch_per_gpu": B, "global_batch": B * world,
-                   "model_arch": args.model_arch, "parallelism": f"dp{world}",
+                   "model_arch": args.model_arch, "parallelism": f"dp{world}", "cuda_graphs": bool(tr.use_graphs),
                    "l2": "per-step working set (weights+grads+Adam moments+activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "image-pairs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / steps},

@@ -274,6 +274,9 @@ struct WgradParams {
   int Cs, Cb, m_tiles, n_tiles;
   int splits, chunks_per_split;
   float* ws;  // [split][m_tile][n_tile][half][128][512]
+  float* dw;  // direct mode (splits == 1): the epilogue writes dw = beta*dw + acc in PyTorch layout itself
+  float beta;
+  int direct;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -378,19 +381,46 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    float* dst = p.ws + ((((size_t)split * p.m_tiles + mt) * p.n_tiles + nt) * 2 + half) * (size_t)(128 * 512) +
-                 (size_t)row * 512;
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c = 0; c < 512; c += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(taddr + c, r);
-      tmem_ld_wait();
+    if (p.direct) {
+      // dw[cs][cb][half*8 .. half*8+7]: the 8 taps of one (cs, cb) sit in 8 TMEM column blocks of this lane
+      float* drow = p.dw + (((size_t)(mt * 128 + row)) * p.Cb + (size_t)nt * 64) * 16 + half * 8;
+      for (int c8 = 0; c8 < 64; c8 += 8) {
+        uint32_t r[8][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        *reinterpret_cast<uint4*>(dst + c + 4 * j) = v;
+        for (int t = 0; t < 8; ++t) tmem_ld_32x8(taddr + (uint32_t)(t * 64 + c8), r[t]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float* d = drow + (size_t)(c8 + j) * 16;
+          float4 o0 = make_float4(__uint_as_float(r[0][j]), __uint_as_float(r[1][j]), __uint_as_float(r[2][j]),
+                                  __uint_as_float(r[3][j]));
+          float4 o1 = make_float4(__uint_as_float(r[4][j]), __uint_as_float(r[5][j]), __uint_as_float(r[6][j]),
+                                  __uint_as_float(r[7][j]));
+          if (p.beta != 0.f) {
+            const float4 a0 = *reinterpret_cast<const float4*>(d);
+            const float4 a1 = *reinterpret_cast<const float4*>(d + 4);
+            o0.x += p.beta * a0.x; o0.y += p.beta * a0.y; o0.z += p.beta * a0.z; o0.w += p.beta * a0.w;
+            o1.x += p.beta * a1.x; o1.y += p.beta * a1.y; o1.z += p.beta * a1.z; o1.w += p.beta * a1.w;
+          }
+          *reinterpret_cast<float4*>(d) = o0;
+          *reinterpret_cast<float4*>(d + 4) = o1;
+        }
+      }
+    } else {
+      float* dst = p.ws + ((((size_t)split * p.m_tiles + mt) * p.n_tiles + nt) * 2 + half) * (size_t)(128 * 512) +
+                   (size_t)row * 512;
+      for (int c = 0; c < 512; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 v = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          *reinterpret_cast<uint4*>(dst + c + 4 * j) = v;
+        }
       }
     }
   }
@@ -597,8 +627,11 @@ int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta
   DG_CHECK_ARG(Hs * Ws * 1LL >= 1 && (Hs * Ws >= kWgKC || (kWgKC % (Hs * Ws)) == 0), "wgrad: bad spatial size");
   WgradParams p;
   wgrad_plan(B, Hs, Ws, Cs, Cb, &p);
-  const size_t need = (size_t)p.splits * p.m_tiles * p.n_tiles * 2 * 128 * 512 * sizeof(float);
-  DG_CHECK_ARG(ws != nullptr && ws_bytes >= need, "wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
+  p.direct = p.splits == 1;
+  p.dw = dw;
+  p.beta = beta;
+  const size_t need = p.direct ? 0 : (size_t)p.splits * p.m_tiles * p.n_tiles * 2 * 128 * 512 * sizeof(float);
+  DG_CHECK_ARG(p.direct || (ws != nullptr && ws_bytes >= need), "wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
   DG_CHECK_ARG(((uintptr_t)small & 15) == 0 && ((uintptr_t)big & 15) == 0 && ((uintptr_t)dw & 15) == 0 &&
                    ((uintptr_t)ws & 15) == 0,
                "wgrad: pointers must be 16-byte aligned");
@@ -621,6 +654,7 @@ int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta
   dim3 grid(p.m_tiles * p.n_tiles * 2, p.splits);
   wgrad_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmS, tmBig, p);
   DG_CHECK_LAUNCH("wgrad_gemm_kernel");
+  if (p.direct) return DG_OK;
   const long long total = (long long)Cs * Cb * 2;
   wgrad_reduce_kernel<<<dg_ceil_div(total, 256), 256, 0, stream>>>(p.ws, dw, beta, Cs, Cb, p.m_tiles, p.n_tiles,
                                                                    p.splits);

@@ -102,7 +102,7 @@ struct BnGeom {
   int rows_split;  // rows per split (multiple of rows_iter)
 };
 
-BnGeom bn_geom(long long P, int C, int vec, int sms) {
+BnGeom bn_geom(long long P, int C, int vec, int sms, int blocks_per_sm = 4) {
   BnGeom g;
   const int cv = (C + vec - 1) / vec;
   int cw = 1;
@@ -110,11 +110,11 @@ BnGeom bn_geom(long long P, int C, int vec, int sms) {
   g.cw = cw;
   g.rows_iter = 256 / cw;
   g.gx = (cv + cw - 1) / cw;
-  long long want = (4LL * sms + g.gx - 1) / g.gx;
+  long long want = ((long long)blocks_per_sm * sms + g.gx - 1) / g.gx;
   long long max_splits = (P + g.rows_iter * 4 - 1) / (g.rows_iter * 4);
   if (want > max_splits) want = max_splits;
   if (want < 1) want = 1;
-  if (want > 1024) want = 1024;
+  if (want > 2048) want = 2048;
   long long rs = (P + want - 1) / want;
   rs = (rs + g.rows_iter - 1) / g.rows_iter * g.rows_iter;
   g.rows_split = (int)rs;
@@ -180,7 +180,20 @@ bn_stats_partial_kernel(const bf16* __restrict__ z, long long P, int C, int cw, 
   if (c < C) {
     const long long r0 = (long long)blockIdx.y * rows_split;
     const long long r1 = min(P, r0 + rows_split);
-    for (long long r = r0 + ty; r < r1; r += rows_iter) {
+    long long r = r0 + ty;
+    for (; r + 3LL * rows_iter < r1; r += 4LL * rows_iter) {   // 4 independent 16-byte loads in flight
+      float f[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load_vec<VEC>(z + (r + (long long)u * rows_iter) * C + c, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          s1[i] += f[u][i];
+          s2[i] += f[u][i] * f[u][i];
+        }
+    }
+    for (; r < r1; r += rows_iter) {
       float f[VEC];
       load_vec<VEC>(z + r * C + c, f);
 #pragma unroll
@@ -249,19 +262,40 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
-bn_act_fwd_kernel(const bf16* __restrict__ z, bf16* __restrict__ y, long long P, int C,
-                  const float* __restrict__ scale, const float* __restrict__ shift, int act, float slope) {
-  const int cv = (C + VEC - 1) / VEC;
-  const long long total = P * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * VEC;
-    const long long off = (i / cv) * C + c;
-    float f[VEC];
-    load_vec<VEC>(z + off, f);
+bn_act_fwd_kernel(const bf16* __restrict__ z, bf16* __restrict__ y, long long P, int C, int cw, int rows_iter,
+                  int rows_split, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                  float slope) {
+  // same (channel vectors) x (rows) block shape as the reductions: a thread keeps its channels' coefficients in
+  // registers and streams rows -- no per-element index arithmetic
+  const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
+  const int c = (blockIdx.x * cw + tx) * VEC;
+  if (c >= C) return;
+  float sc[VEC], sh[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) f[k] = act_fwd(f[k] * scale[c + k] + shift[c + k], act, slope);
-    store_vec<VEC>(y + off, f);
+  for (int i = 0; i < VEC; ++i) {
+    sc[i] = scale[c + i];
+    sh[i] = shift[c + i];
+  }
+  const long long r0 = (long long)blockIdx.y * rows_split;
+  const long long r1 = min(P, r0 + rows_split);
+  long long r = r0 + ty;
+  for (; r + 3LL * rows_iter < r1; r += 4LL * rows_iter) {
+    float f[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load_vec<VEC>(z + (r + (long long)u * rows_iter) * C + c, f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) f[u][k] = act_fwd(f[u][k] * sc[k] + sh[k], act, slope);
+      store_vec<VEC>(y + (r + (long long)u * rows_iter) * C + c, f[u]);
+    }
+  }
+  for (; r < r1; r += rows_iter) {
+    float f[VEC];
+    load_vec<VEC>(z + r * C + c, f);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) f[k] = act_fwd(f[k] * sc[k] + sh[k], act, slope);
+    store_vec<VEC>(y + r * C + c, f);
   }
 }
 
@@ -309,7 +343,23 @@ bn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2,
     }
     const long long r0 = (long long)blockIdx.y * rows_split;
     const long long r1 = min(P, r0 + rows_split);
-    for (long long r = r0 + ty; r < r1; r += rows_iter) {
+    long long r = r0 + ty;
+    for (; r + rows_iter < r1; r += 2LL * rows_iter) {   // two rows (6 independent loads) in flight
+      float g[2][VEC], fz[2][VEC];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, y, r + (long long)u * rows_iter, C, c, act, slope, g[u]);
+        load_vec<VEC>(z + (r + (long long)u * rows_iter) * C + c, fz[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          s1[i] += g[u][i];
+          s2[i] += g[u][i] * (fz[u][i] - mu[i]) * is[i];
+        }
+    }
+    for (; r < r1; r += rows_iter) {
       float g[VEC], fz[VEC];
       bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, y, r, C, c, act, slope, g);
       load_vec<VEC>(z + r * C + c, fz);
@@ -361,21 +411,42 @@ __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const float* __restrict__ bcast, float coef,
                  long long bcast_rows, const bf16* __restrict__ y, const bf16* __restrict__ z,
                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coefs,
-                 bf16* __restrict__ dz, long long P, int C, int act, float slope) {
-  const int cv = (C + VEC - 1) / VEC;
-  const long long total = P * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * VEC;
-    const long long r = i / cv;
+                 bf16* __restrict__ dz, long long P, int C, int cw, int rows_iter, int rows_split, int act, float slope) {
+  const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
+  const int c = (blockIdx.x * cw + tx) * VEC;
+  if (c >= C) return;
+  float mu[VEC], is[VEC], k0[VEC], k1[VEC], k2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    mu[i] = mean[c + i];
+    is[i] = invstd[c + i];
+    k0[i] = coefs[c + i];
+    k1[i] = coefs[C + c + i];
+    k2[i] = coefs[2 * C + c + i];
+  }
+  const long long r0 = (long long)blockIdx.y * rows_split;
+  const long long r1 = min(P, r0 + rows_split);
+  long long r = r0 + ty;
+  for (; r + rows_iter < r1; r += 2LL * rows_iter) {
+    float g[2][VEC], fz[2][VEC];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, y, r + (long long)u * rows_iter, C, c, act, slope, g[u]);
+      load_vec<VEC>(z + (r + (long long)u * rows_iter) * C + c, fz[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) g[u][k] = k0[k] * (g[u][k] - k1[k] - (fz[u][k] - mu[k]) * is[k] * k2[k]);
+      store_vec<VEC>(dz + (r + (long long)u * rows_iter) * C + c, g[u]);
+    }
+  }
+  for (; r < r1; r += rows_iter) {
     float g[VEC], fz[VEC];
     bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, y, r, C, c, act, slope, g);
     load_vec<VEC>(z + r * C + c, fz);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const float xhat = (fz[k] - mean[c + k]) * invstd[c + k];
-      g[k] = coefs[c + k] * (g[k] - coefs[C + c + k] - xhat * coefs[2 * C + c + k]);
-    }
+    for (int k = 0; k < VEC; ++k) g[k] = k0[k] * (g[k] - k1[k] - (fz[k] - mu[k]) * is[k] * k2[k]);
     store_vec<VEC>(dz + r * C + c, g);
   }
 }
@@ -691,12 +762,15 @@ int dg_bn_eval_coeffs(const float* gamma, const float* beta, const float* runnin
 int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats, int act, float slope,
                   cudaStream_t stream) {
   DG_CHECK_ARG(P > 0 && C > 0 && z && y && stats, "bn_act_fwd: bad args");
-  if (C % 8 == 0)
-    bn_act_fwd_kernel<8><<<ew_grid(P * (C / 8), sms()), 256, 0, stream>>>((const bf16*)z, (bf16*)y, P, C, stats + 2 * C,
-                                                                         stats + 3 * C, act, slope);
+  const int vec = (C % 8 == 0) ? 8 : 1;
+  BnGeom g = bn_geom(P, C, vec, sms(), 8);
+  dim3 grid(g.gx, g.gy);
+  if (vec == 8)
+    bn_act_fwd_kernel<8><<<grid, 256, 0, stream>>>((const bf16*)z, (bf16*)y, P, C, g.cw, g.rows_iter, g.rows_split,
+                                                   stats + 2 * C, stats + 3 * C, act, slope);
   else
-    bn_act_fwd_kernel<1><<<ew_grid(P * C, sms()), 256, 0, stream>>>((const bf16*)z, (bf16*)y, P, C, stats + 2 * C,
-                                                                   stats + 3 * C, act, slope);
+    bn_act_fwd_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)z, (bf16*)y, P, C, g.cw, g.rows_iter, g.rows_split,
+                                                   stats + 2 * C, stats + 3 * C, act, slope);
   DG_CHECK_LAUNCH("bn_act_fwd");
   return DG_OK;
 }
@@ -728,14 +802,16 @@ int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bca
   bn_bwd_finalize_kernel<<<dg_ceil_div(C, 32), 256, 0, stream>>>(pg, pgx, g.gy, P, C, gamma, invstd, dgamma, dbeta,
                                                                   grad_beta, coefs);
   DG_CHECK_LAUNCH("bn_bwd_finalize");
+  BnGeom g2 = bn_geom(P, C, vec, sms(), 8);
+  dim3 grid2(g2.gx, g2.gy);
   if (vec == 8)
-    bn_bwd_dx_kernel<8><<<ew_grid(P * (C / 8), sms()), 256, 0, stream>>>(
-        (const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows, (const bf16*)y, (const bf16*)z, mean, invstd,
-        coefs, (bf16*)dz, P, C, act, slope);
+    bn_bwd_dx_kernel<8><<<grid2, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
+                                                   (const bf16*)y, (const bf16*)z, mean, invstd, coefs, (bf16*)dz, P, C,
+                                                   g2.cw, g2.rows_iter, g2.rows_split, act, slope);
   else
-    bn_bwd_dx_kernel<1><<<ew_grid(P * C, sms()), 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef,
-                                                                  bcast_rows, (const bf16*)y, (const bf16*)z, mean,
-                                                                  invstd, coefs, (bf16*)dz, P, C, act, slope);
+    bn_bwd_dx_kernel<1><<<grid2, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
+                                                   (const bf16*)y, (const bf16*)z, mean, invstd, coefs, (bf16*)dz, P, C,
+                                                   g2.cw, g2.rows_iter, g2.rows_split, act, slope);
   DG_CHECK_LAUNCH("bn_bwd_dx");
   return DG_OK;
 }

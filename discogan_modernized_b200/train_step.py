@@ -184,6 +184,8 @@ class DiscoGANTrainer:
         self._static = {}        # batch -> (A, B) static input buffers
         self._pool = None
         self._scratch_gen = -1
+        self._graph_launches = {}   # kernels inside each captured graph
+        self.kernel_launches = 0    # kernels of this library launched (eagerly or by graph replay) by step()
 
     # ------------------------------------------------------------------------------------------
     def _disc_pair(self, D, real_img, fake_img, slot, save_real, save_fake):
@@ -210,8 +212,11 @@ class DiscoGANTrainer:
         discriminator step.  Losses of the iteration are in ``self.loss_buf`` (see ``losses()``)."""
         is_dis = self.iters % self.update_interval == 0
         rate = self.starting_rate if self.iters < self.gan_curriculum else self.default_rate
+        from ._lib import lib
+        count0 = lib().dg_launch_count()
         if not self.use_graphs:
             self._step_impl(A, B, is_dis, rate)
+            self.kernel_launches += lib().dg_launch_count() - count0
         else:
             if self._scratch_gen != ops.scratch_generation and self._graphs:
                 self._graphs.clear()            # a scratch buffer moved: captured pointers are stale
@@ -222,6 +227,7 @@ class DiscoGANTrainer:
                 # first encounter: run eagerly (sizes scratch buffers, sets kernel attributes), capture next time
                 self._step_impl(A, B, is_dis, rate)
                 self._eager_done.add(key)
+                self.kernel_launches += lib().dg_launch_count() - count0
             else:
                 st = self._static.get(A.shape[0])
                 if st is None:
@@ -237,8 +243,10 @@ class DiscoGANTrainer:
                     with torch.cuda.graph(g, pool=self._pool):
                         self._step_impl(st[0], st[1], is_dis, rate)
                     self._graphs[key] = g
+                    self._graph_launches[key] = lib().dg_launch_count() - count0
                     self._scratch_gen = ops.scratch_generation
                 g.replay()
+                self.kernel_launches += self._graph_launches[key]
         self.iters += 1
         return is_dis
 
