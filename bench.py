@@ -209,33 +209,50 @@ def timed_steps_e2e(tr, host_batches, steps, torch, dist, world):
 
 
 def measure_roofline(tr, batches, torch, pk):
-    """Per-launch CUDA-event timing of the tensor-core convolution kernels over one D,G,G cycle (separate from
-    the throughput region so the events do not perturb it)."""
+    """Per-launch CUDA-event timing over one D,G,G cycle, eager launches on the trainer's stream (separate from the
+    throughput region so the events do not perturb it).  Tensor-bound: the tcgen05 convolution kernels, algorithmic
+    FLOPs 2*B*Ho*Wo*Co*Ci*16 per launch.  HBM-bound: BatchNorm(+activation) forward/backward and Adam, algorithmic
+    bytes per DESIGN.md section 3.4."""
     from discogan_modernized_b200 import ops
     recs = []
-    orig = {n: getattr(ops, n) for n in ("conv_down", "conv_up", "conv_wgrad")}
 
-    def wrap(name, fn):
+    def conv_work(name, a):
+        if name in ("conv_down", "conv_down_stats"):
+            big, wd = a[0], a[1]
+            return "conv_gemm", conv_flops(big.shape[0], big.shape[1] // 2, wd.shape[0], big.shape[3]), \
+                f"down B{big.shape[0]} {big.shape[1]}->{big.shape[1] // 2} {big.shape[3]}->{wd.shape[0]}"
+        if name in ("conv_up", "conv_up_stats"):
+            small, wu = a[0], a[1]
+            return "conv_gemm", conv_flops(small.shape[0], small.shape[1], small.shape[3], wu.shape[0]), \
+                f"up B{small.shape[0]} {small.shape[1]}->{2 * small.shape[1]} {small.shape[3]}->{wu.shape[0]}"
+        small, big = a[0], a[1]
+        return "conv_wgrad", conv_flops(small.shape[0], small.shape[1], small.shape[3], big.shape[3]), \
+            f"wgrad B{small.shape[0]} {small.shape[1]} {small.shape[3]}x{big.shape[3]}"
+
+    def hbm_work(name, a):
+        if name == "bn_act_fwd":
+            return "bn_act_fwd", 4.0 * a[0].numel(), ""            # read z, write y (bf16)
+        if name == "bn_act_bwd":
+            return "bn_act_bwd", 14.0 * a[0].numel(), ""           # reduce: dy,y,z ; dx: dy,y,z + write dz
+        return "adam", 28.0 * a[0].numel(), ""                     # p,g,m,v read + p,m,v write (fp32); +repack excluded
+
+    names = {n: conv_work for n in ("conv_down", "conv_up", "conv_wgrad", "conv_down_stats", "conv_up_stats")}
+    names.update({n: hbm_work for n in ("bn_act_fwd", "bn_act_bwd", "adam_step")})
+    orig = {n: getattr(ops, n) for n in names}
+
+    def wrap(name, fn, work):
         def inner(*a, **k):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             out = fn(*a, **k)
             e.record()
-            if name == "conv_down":
-                big, wd = a[0], a[1]
-                fl = conv_flops(big.shape[0], big.shape[1] // 2, wd.shape[0], big.shape[3])
-            elif name == "conv_up":
-                small, wu = a[0], a[1]
-                fl = conv_flops(small.shape[0], small.shape[1], small.shape[3], wu.shape[0])
-            else:
-                small, big = a[0], a[1]
-                fl = conv_flops(small.shape[0], small.shape[1], small.shape[3], big.shape[3])
-            recs.append((name, fl, s, e))
+            cls, amount, label = work(name, a)
+            recs.append((cls, amount, label, s, e))
             return out
         return inner
 
     for n, f in orig.items():
-        setattr(ops, n, wrap(n, f))
+        setattr(ops, n, wrap(n, f, names[n]))
     saved_graphs = tr.use_graphs
     tr.use_graphs = False                      # per-launch events need eager launches
     try:
@@ -247,23 +264,31 @@ def measure_roofline(tr, batches, torch, pk):
         tr.use_graphs = saved_graphs
         for n, f in orig.items():
             setattr(ops, n, f)
-    by = {}
-    for name, fl, s, e in recs:
-        d = by.setdefault(name, [0.0, 0.0, 0])
-        d[0] += fl
-        d[1] += s.elapsed_time(e) * 1e-3
-        d[2] += 1
+    by, layers = {}, {}
+    for cls, amount, label, s, e in recs:
+        sec = s.elapsed_time(e) * 1e-3
+        d = by.setdefault(cls, [0.0, 0.0, 0])
+        d[0] += amount; d[1] += sec; d[2] += 1
+        if label:
+            l = layers.setdefault(label, [0.0, 0.0, 0])
+            l[0] += amount; l[1] += sec; l[2] += 1
     out = {}
-    for name, (fl, sec, n) in by.items():
-        out[name] = {"launches": n, "tflops": fl / sec / 1e12 if sec > 0 else 0.0, "avg_us": sec / n * 1e6, "seconds": sec}
-    gemm_fl = sum(by[n][0] for n in ("conv_down", "conv_up") if n in by)
-    gemm_s = sum(by[n][1] for n in ("conv_down", "conv_up") if n in by)
-    gemm_n = sum(by[n][2] for n in ("conv_down", "conv_up") if n in by)
-    ach = gemm_fl / gemm_s / 1e12 if gemm_s > 0 else 0.0
+    for cls, (amount, sec, n) in by.items():
+        if cls.startswith("conv"):
+            out[cls] = {"launches": n, "tflops": amount / sec / 1e12, "avg_us": sec / n * 1e6, "ms_per_cycle": sec * 1e3,
+                        "frac_of_tensor_peak": amount / sec / 1e12 / pk["tf_sustained"]}
+        else:
+            out[cls] = {"launches": n, "gbs": amount / sec / 1e9, "avg_us": sec / n * 1e6, "ms_per_cycle": sec * 1e3,
+                        "frac_of_hbm_peak": amount / sec / 1e9 / pk["hbm"]}
+    top = sorted(layers.items(), key=lambda kv: -kv[1][1])[:12]
+    out["layers"] = {k: {"launches": n, "tflops": round(a / sec / 1e12, 1), "ms_per_cycle": round(sec * 1e3, 3)}
+                     for k, (a, sec, n) in top}
+    g = by.get("conv_gemm", [0.0, 1.0, 1])
+    ach = g[0] / g[1] / 1e12
     roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: conv fprop/dgrad, convT fprop/dgrad)",
             "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
             "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside the step)", "traffic": None,
-            "launches_per_cycle": gemm_n, "avg_launch_us": gemm_s / max(gemm_n, 1) * 1e6,
+            "launches_per_cycle": g[2], "avg_launch_us": g[1] / max(g[2], 1) * 1e6,
             "algorithmic": "2*B*Ho*Wo*Co*Ci*16 FLOP per launch"}
     return roof, out
 

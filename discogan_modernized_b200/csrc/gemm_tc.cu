@@ -51,7 +51,27 @@ struct ConvGemmParams {
   float mask_slope;
   float* img;         // epilogue "image": 3 real output channels written as fp32 NCHW planes instead of `out`
   int img_sigmoid, img_accumulate;
+  float* stat_part;   // BatchNorm statistics fused in the epilogue: per-CTA partial sums [2][gridDim.x][N] of the fp32
+                      // accumulators (sum, sum of squares) over the rows this CTA produced; NULL = off
 };
+
+// Sum the 32 values each lane holds for 32 columns over the 32 lanes (rows) of the warp: afterwards v[0] of lane l is
+// the column-(l) total.  Butterfly reduce-scatter, 31 shuffles.
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int d = 16, n = 16; d >= 1; d >>= 1, n >>= 1) {
+    const bool upper = (lane & d) != 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < n) {
+        const float send = upper ? v[j] : v[j + n];
+        const float keep = upper ? v[j + n] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+      }
+    }
+  }
+  return v[0];
+}
 
 struct TileCoord {
   int par, nt, b0, h0, w0;
@@ -86,6 +106,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_stat = reinterpret_cast<float*>(bars + 32);   // [2][N] when p.stat_part
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -184,6 +205,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (p.stat_part) {
+      for (int i = threadIdx.x - 64; i < 2 * p.N; i += 128) s_stat[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int wl = row % p.Wt;
@@ -226,6 +251,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           tmem_ld_32x32(taddr + c, r);
           tmem_ld_wait();
+          if (p.stat_part) {   // rows beyond the batch are exact zeros (TMA zero fill), so no masking is needed
+            float v[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+            const float cs = warp_column_sums(v, lane);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) * __uint_as_float(r[e]);
+            const float cq = warp_column_sums(v, lane);
+            const int n = t.nt * p.block_n + c + lane;
+            atomicAdd(&s_stat[n], cs);
+            atomicAdd(&s_stat[p.N + n], cq);
+          }
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -248,6 +285,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
+    if (p.stat_part) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* ps = p.stat_part + (size_t)blockIdx.x * p.N;
+      float* pq = p.stat_part + ((size_t)gridDim.x + blockIdx.x) * p.N;
+      for (int i = threadIdx.x - 64; i < p.N; i += 128) {
+        ps[i] = s_stat[i];
+        pq[i] = s_stat[p.N + i];
+      }
     }
   }
 
@@ -476,6 +522,8 @@ struct ConvGemmExtras {
   float mask_slope = 0.f;
   float* img = nullptr;  // when set: Cb (mode 1 output channels) is the padded 16 and only 3 planes are written
   int img_sigmoid = 0, img_accumulate = 0;
+  float* stat_part = nullptr;  // [2][grid][N] partial BatchNorm sums
+  int* grid_out = nullptr;     // plan query: receives the grid size, nothing is launched
 };
 
 int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, int B, int Hs, int Ws, int Cs, int Cb,
@@ -521,11 +569,18 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   p.img = ex.img;
   p.img_sigmoid = ex.img_sigmoid;
   p.img_accumulate = ex.img_accumulate;
+  p.stat_part = ex.stat_part;
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  if (ex.grid_out) {
+    *ex.grid_out = grid;
+    return DG_OK;
+  }
   const int stage_bytes = kATileBytes + bn * 128;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
-  const int smem_bytes = stages * stage_bytes + 1024 + 256;
+  const int smem_bytes = stages * stage_bytes + 1024 + 256 + (ex.stat_part ? 2 * N * (int)sizeof(float) : 0);
+  DG_CHECK_ARG(smem_bytes <= 227 * 1024, "conv gemm: N=%d too wide for fused statistics", N);
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -548,7 +603,6 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     }
     attr_set = true;
   }
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
   DG_CHECK_LAUNCH("conv_gemm_kernel");
   return DG_OK;
@@ -589,6 +643,31 @@ int dg_conv4x4s2_fprop(const void* x, const void* wd, void* z, int B, int H, int
 int dg_conv4x4s2_dgrad(const void* dz, const void* wu, void* dx, int B, int Hs, int Ws, int Cs, int Cb,
                        cudaStream_t stream) {
   return launch_conv_gemm(1, dz, wu, dx, B, Hs, Ws, Cs, Cb, stream);
+}
+
+// Forward convolutions with the BatchNorm statistics of their output fused in the epilogue.
+// mode 0 = Conv2d fprop (x big -> z small), mode 1 = ConvTranspose2d fprop (x small -> z big).
+// stat_part: float[2 * rows * N] with rows = dg_conv_stats_rows(...), N = output channels; feed dg_bn_stats_finalize.
+int dg_conv_stats_rows(int mode, int B, int Hs, int Ws, int Cs, int Cb) {
+  int grid = 0;
+  ConvGemmExtras ex;
+  ex.grid_out = &grid;
+  if (launch_conv_gemm(mode, (const void*)16, (const void*)16, (void*)16, B, Hs, Ws, Cs, Cb, 0, ex) != DG_OK) return 0;
+  return grid;
+}
+int dg_conv4x4s2_fprop_stats(const void* x, const void* wd, void* z, float* stat_part, int B, int H, int W, int Cb,
+                             int Cs, cudaStream_t stream) {
+  DG_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && stat_part, "fprop_stats: bad args");
+  ConvGemmExtras ex;
+  ex.stat_part = stat_part;
+  return launch_conv_gemm(0, x, wd, z, B, H / 2, W / 2, Cs, Cb, stream, ex);
+}
+int dg_convT4x4s2_fprop_stats(const void* x_small, const void* wu, void* y_big, float* stat_part, int B, int Hs, int Ws,
+                              int Cs, int Cb, cudaStream_t stream) {
+  DG_CHECK_ARG(stat_part != nullptr, "convT_fprop_stats: bad args");
+  ConvGemmExtras ex;
+  ex.stat_part = stat_part;
+  return launch_conv_gemm(1, x_small, wu, y_big, B, Hs, Ws, Cs, Cb, stream, ex);
 }
 
 // dgrad whose consumer is a BN-less LeakyReLU layer: dx = dgrad * (mask > 0 ? 1 : slope), mask = that layer's output

@@ -749,6 +749,20 @@ int dg_bn_stats(const void* z, long long P, int C, const float* gamma, const flo
   return DG_OK;
 }
 
+// Finish statistics whose partial sums were produced elsewhere (the fused conv epilogue): part = float[2*rows*C]
+// {sum rows, sum-of-squares rows}.  Same outputs / running-stat update as dg_bn_stats.
+int dg_bn_stats_finalize(const float* part, int rows, long long P, int C, const float* gamma, const float* beta,
+                         float eps, float momentum, float* stats, float* running_mean, float* running_var,
+                         cudaStream_t stream) {
+  DG_CHECK_ARG(part && rows > 0 && P > 0 && C > 0 && stats, "bn_stats_finalize: bad args");
+  bn_stats_finalize_kernel<<<dg_ceil_div(C, 32), 256, 0, stream>>>(part, part + (size_t)rows * C, rows, P, C, eps,
+                                                                   momentum, gamma, beta, stats, stats + C,
+                                                                   stats + 2 * C, stats + 3 * C, running_mean,
+                                                                   running_var);
+  DG_CHECK_LAUNCH("bn_stats_finalize");
+  return DG_OK;
+}
+
 int dg_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                       float eps, int C, float* stats, cudaStream_t stream) {
   DG_CHECK_ARG(C > 0 && stats, "bn_eval_coeffs: bad args");

@@ -85,10 +85,15 @@ def _new_packed():
 
 
 def _grad_buf(p):
-    """fp32 gradient buffer of a parameter (allocated zeroed on first use, then accumulated into)."""
+    """(fp32 gradient buffer of a parameter, beta): the kernels compute grad = beta*grad + new.  A missing buffer is
+    allocated zeroed (beta 1, autograd's accumulate semantics).  The fused trainer marks its flat gradient views
+    ``_dg_fresh`` instead of zero-filling them: the first write of an iteration then overwrites (beta 0)."""
+    if getattr(p, "_dg_fresh", False) and p.grad is not None:
+        p._dg_fresh = False
+        return p.grad, 0.0
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
-    return p.grad
+    return p.grad, 1.0
 
 
 def _check_input(x, image_size, training):
@@ -109,16 +114,27 @@ class _BnSave:
         self.z, self.y, self.stats = z, y, stats
 
 
-def _bn_act(z, bn, act, training):
-    """z: NHWC bf16 (any leading dims, channels last).  Returns (y, stats)."""
+def _conv_bn(conv_fn, conv_stats_fn, x, w, training):
+    """Run a GEMM convolution; in training mode its epilogue also produces the partial BatchNorm sums."""
+    if training and ops._conv_impl == "tc":
+        return conv_stats_fn(x, w)
+    return conv_fn(x, w), None
+
+
+def _bn_act(z, bn, act, training, part=None):
+    """z: NHWC bf16 (any leading dims, channels last); part: partial sums from the producing conv's epilogue.
+    Returns (y, stats)."""
     C = z.shape[-1]
     z2 = z.view(-1, C)
     if training or not bn.track_running_stats:
         if z2.shape[0] < 2:
             raise ValueError("Expected more than 1 value per channel when training")
         rm, rv = (bn.running_mean, bn.running_var) if (training and bn.track_running_stats) else (None, None)
-        stats = ops.bn_stats(z2, bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps,
-                             bn.momentum if bn.momentum is not None else 0.1)
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        if part is not None:
+            stats = ops.bn_stats_finalize(part, z2.shape[0], bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, mom)
+        else:
+            stats = ops.bn_stats(z2, bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, mom)
         if rm is not None:
             bn.num_batches_tracked.add_(1)
     else:
@@ -129,17 +145,18 @@ def _bn_act(z, bn, act, training):
 
 def _bn_act_bwd(dy, sv, bn, act, need_wgrad, dy2=None, bcast=None, bcast_coef=0.0):
     C = sv.z.shape[-1]
-    dgamma = _grad_buf(bn.weight) if need_wgrad else None
-    dbeta = _grad_buf(bn.bias) if need_wgrad else None
+    dgamma, gb = _grad_buf(bn.weight) if need_wgrad else (None, 1.0)
+    dbeta, gb2 = _grad_buf(bn.bias) if need_wgrad else (None, 1.0)
+    assert gb == gb2
     dz = ops.bn_act_bwd(dy.view(-1, C), sv.y.view(-1, C), sv.z.view(-1, C), sv.stats, bn.weight.detach(), act,
-                        LRELU_SLOPE, dgamma, dbeta, 1.0, None if dy2 is None else dy2.view(-1, C), bcast, bcast_coef)
+                        LRELU_SLOPE, dgamma, dbeta, gb, None if dy2 is None else dy2.view(-1, C), bcast, bcast_coef)
     return dz.view(sv.z.shape)
 
 
 def _conv1_backward(pk, weight, ctx, dz1, need_dx, need_wgrad, dx_out, dx_accumulate):
     """Backward of the image-side Conv2d(3,64,4,2,1)+LeakyReLU given dz1 = d(loss)/d(pre-activation)."""
     if need_wgrad:
-        ops.c3_wgrad_tc(dz1, ctx.xp, _grad_buf(weight), 1.0)
+        ops.c3_wgrad_tc(dz1, ctx.xp, *_grad_buf(weight))
     if not need_dx:
         return None
     _, wu3 = pk.get_c3(weight)
@@ -168,8 +185,8 @@ def discriminator_forward(mod, x, save=True):
     for k in range(2, mod.n_down + 1):
         conv, bn = getattr(mod, f"conv{k}"), getattr(mod, f"bn{k}")
         wd, _ = pk.get(conv.weight, True, True)
-        z = ops.conv_down(y, wd)
-        y, stats = _bn_act(z, bn, ACT_LRELU, training)
+        z, part = _conv_bn(ops.conv_down, ops.conv_down_stats, y, wd, training)
+        y, stats = _bn_act(z, bn, ACT_LRELU, training, part)
         ctx.bn.append(_BnSave(z if save else None, y, stats))
         feats.append(y)
     head = getattr(mod, f"conv{mod.n_down + 1}")
@@ -189,7 +206,7 @@ def discriminator_backward(mod, ctx, dlogit, dfeats=None, fm_bcast=None, need_dx
     y_last = ctx.bn[-1].y
     dl = dlogit.contiguous().view(B, 1)
     if need_wgrad:
-        ops.fc_wgrad(dl, y_last.view(B, -1), _grad_buf(head.weight), 1.0)
+        ops.fc_wgrad(dl, y_last.view(B, -1), *_grad_buf(head.weight))
     dy = ops.fc_up(dl, wd.view(1, -1)).view(y_last.shape)
     for k in range(mod.n_down, 1, -1):
         i = k - 2
@@ -200,7 +217,7 @@ def discriminator_backward(mod, ctx, dlogit, dfeats=None, fm_bcast=None, need_dx
         dz = _bn_act_bwd(dy, sv, bn, ACT_LRELU, need_wgrad, dy2, bc, coef)
         y_prev = ctx.bn[i - 1].y if i > 0 else ctx.y1
         if need_wgrad:
-            ops.conv_wgrad(dz, y_prev, _grad_buf(conv.weight), 1.0)
+            ops.conv_wgrad(dz, y_prev, *_grad_buf(conv.weight))
         _, wu = pk.get(conv.weight, True, True)
         # the gradient reaching conv1's output also takes conv1's LeakyReLU derivative (fused in the epilogue)
         dy = ops.conv_up(dz, wu, mask=ctx.y1 if i == 0 else None, slope=LRELU_SLOPE)
@@ -309,8 +326,8 @@ def generator_forward(mod, x, save=True):
     ctx.y1, ctx.enc = y, []
     for conv, bn in zip(enc_convs[1:], enc_bns[1:]):
         wd, _ = pk.get(conv.weight, True, True)
-        z = ops.conv_down(y, wd)
-        y, stats = _bn_act(z, bn, ACT_LRELU, training)
+        z, part = _conv_bn(ops.conv_down, ops.conv_down_stats, y, wd, training)
+        y, stats = _bn_act(z, bn, ACT_LRELU, training, part)
         ctx.enc.append(_BnSave(z if save else None, y, stats))
     # 4x4 valid conv to the 100-d bottleneck (model.py:107-109)
     wd, _ = pk.get(head_conv.weight, True, False)
@@ -326,8 +343,8 @@ def generator_forward(mod, x, save=True):
     ctx.dec = []
     for conv, bn in zip(dec_convs[1:-1], dec_bns[1:]):
         _, wu = pk.get(conv.weight, True, True)
-        z = ops.conv_up(y, wu)
-        y, stats = _bn_act(z, bn, ACT_RELU, training)
+        z, part = _conv_bn(ops.conv_up, ops.conv_up_stats, y, wu, training)
+        y, stats = _bn_act(z, bn, ACT_RELU, training, part)
         ctx.dec.append(_BnSave(z if save else None, y, stats))
     _, wu3 = pk.get_c3(dec_convs[-1].weight)
     out = ops.c3_up_tc(y, wu3, sigmoid=True)
@@ -344,7 +361,7 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
     last = dec_convs[-1]
     dpre = ops.img_pad_nhwc4(dout.contiguous(), yimg=ctx.out)      # d(loss)/d(pre-sigmoid), padded NHWC4 bf16
     if need_wgrad:
-        ops.c3_wgrad_tc(dec_in[-1].y, dpre, _grad_buf(last.weight), 1.0)
+        ops.c3_wgrad_tc(dec_in[-1].y, dpre, *_grad_buf(last.weight))
     wc_last, _ = pk.get_c3(last.weight)
     dy = ops.c3_down_tc(dpre, wc_last, ops.ACT_NONE)
     for j in range(len(ctx.dec), 0, -1):
@@ -353,20 +370,20 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
         dz = _bn_act_bwd(dy, sv, bn, ACT_RELU, need_wgrad)
         x_in = dec_in[j - 1].y
         if need_wgrad:
-            ops.conv_wgrad(x_in, dz, _grad_buf(conv.weight), 1.0)      # convT wgrad: small = input, big = dz
+            ops.conv_wgrad(x_in, dz, *_grad_buf(conv.weight))      # convT wgrad: small = input, big = dz
         wd, _ = pk.get(conv.weight, True, True)
         dy = ops.conv_down(dz, wd)                                      # convT dgrad
     # decoder.0: ConvTranspose2d(100, C, 4, 1, 0)
     dz = _bn_act_bwd(dy, ctx.dec0, dec_bns[0], ACT_RELU, need_wgrad)
     wd0, _ = pk.get(dec_convs[0].weight, True, False)
     if need_wgrad:
-        ops.fc_wgrad(ctx.head.y, dz.view(B, -1), _grad_buf(dec_convs[0].weight), 1.0)
+        ops.fc_wgrad(ctx.head.y, dz.view(B, -1), *_grad_buf(dec_convs[0].weight))
     dy = ops.fc_down(dz.view(B, -1), wd0.view(wd0.shape[0], -1))
     # encoder head: Conv2d(C, 100, 4, 1, 0)
     dz = _bn_act_bwd(dy, ctx.head, head_bn, ACT_LRELU, need_wgrad)
     y_last = ctx.enc[-1].y
     if need_wgrad:
-        ops.fc_wgrad(dz, y_last.view(B, -1), _grad_buf(head_conv.weight), 1.0)
+        ops.fc_wgrad(dz, y_last.view(B, -1), *_grad_buf(head_conv.weight))
     wdh, _ = pk.get(head_conv.weight, True, False)
     dy = ops.fc_up(dz, wdh.view(wdh.shape[0], -1)).view(y_last.shape)
     for i in range(len(ctx.enc), 0, -1):
@@ -375,7 +392,7 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
         dz = _bn_act_bwd(dy, sv, bn, ACT_LRELU, need_wgrad)
         y_prev = ctx.enc[i - 2].y if i > 1 else ctx.y1
         if need_wgrad:
-            ops.conv_wgrad(dz, y_prev, _grad_buf(conv.weight), 1.0)
+            ops.conv_wgrad(dz, y_prev, *_grad_buf(conv.weight))
         _, wu = pk.get(conv.weight, True, True)
         dy = ops.conv_up(dz, wu, mask=ctx.y1 if i == 1 else None, slope=LRELU_SLOPE)
     return _conv1_backward(pk, enc_convs[0].weight, ctx, dy, need_dx, need_wgrad, dx_out, dx_accumulate)

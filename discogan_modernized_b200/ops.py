@@ -119,6 +119,34 @@ def conv_up(small, wu, mask=None, slope=0.2):
     return out
 
 
+def conv_down_stats(big, wd):
+    """conv_down that also returns per-CTA partial BatchNorm sums of its output: (out, part fp32 [2, rows, Cs])."""
+    B, H, W, Cb = big.shape
+    Cs = wd.shape[0]
+    rows = lib().dg_conv_stats_rows(0, B, H // 2, W // 2, Cs, Cb)
+    if rows <= 0:
+        raise KernelError(f"conv_down_stats: unsupported shape {tuple(big.shape)} x Cs={Cs}")
+    out = torch.empty(B, H // 2, W // 2, Cs, dtype=BF16, device=big.device)
+    part = torch.empty(2, rows, Cs, dtype=F32, device=big.device)
+    check(lib().dg_conv4x4s2_fprop_stats(_ptr(big, BF16, "big"), _ptr(wd, BF16, "wd"), _ptr(out), _ptr(part), B, H, W, Cb,
+                                         Cs, _stream()), "dg_conv4x4s2_fprop_stats")
+    return out, part
+
+
+def conv_up_stats(small, wu):
+    """conv_up (ConvTranspose2d forward) with fused partial BatchNorm sums: (out, part fp32 [2, rows, Cb])."""
+    B, Hs, Ws, Cs = small.shape
+    Cb = wu.shape[0]
+    rows = lib().dg_conv_stats_rows(1, B, Hs, Ws, Cs, Cb)
+    if rows <= 0:
+        raise KernelError(f"conv_up_stats: unsupported shape {tuple(small.shape)} x Cb={Cb}")
+    out = torch.empty(B, 2 * Hs, 2 * Ws, Cb, dtype=BF16, device=small.device)
+    part = torch.empty(2, rows, Cb, dtype=F32, device=small.device)
+    check(lib().dg_convT4x4s2_fprop_stats(_ptr(small, BF16, "small"), _ptr(wu, BF16, "wu"), _ptr(out), _ptr(part), B, Hs,
+                                          Ws, Cs, Cb, _stream()), "dg_convT4x4s2_fprop_stats")
+    return out, part
+
+
 def conv_wgrad(small, big, dw, beta=1.0):
     """dw[Cs,Cb,4,4] = beta*dw + sum_pixels small (x) shifted big."""
     B, Hs, Ws, Cs = small.shape
@@ -266,6 +294,16 @@ def bn_stats(z2d, gamma, beta, running_mean=None, running_var=None, eps=1e-5, mo
     check(lib().dg_bn_stats(_ptr(z2d, BF16, "z"), P, C, _ptr(gamma, F32, "gamma"), _ptr(beta, F32, "beta"), eps, momentum,
                             _ptr(stats), _ptr(running_mean, F32, "running_mean"), _ptr(running_var, F32, "running_var"),
                             sc.data_ptr(), _stream()), "dg_bn_stats")
+    return stats
+
+
+def bn_stats_finalize(part, P, gamma, beta, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
+    """Statistics from partial sums produced by conv_down_stats / conv_up_stats -> stats fp32 [4,C]."""
+    _, rows, C = part.shape
+    stats = torch.empty(4, C, dtype=F32, device=part.device)
+    check(lib().dg_bn_stats_finalize(_ptr(part, F32, "part"), rows, P, C, _ptr(gamma, F32, "gamma"), _ptr(beta, F32, "beta"),
+                                     eps, momentum, _ptr(stats), _ptr(running_mean, F32, "running_mean"),
+                                     _ptr(running_var, F32, "running_var"), _stream()), "dg_bn_stats_finalize")
     return stats
 
 

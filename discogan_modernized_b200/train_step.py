@@ -61,10 +61,13 @@ class FlatNet:
         net._packed.invalidate()
 
     def zero_grad(self):
-        self.flat_g.zero_()
+        """No memset: every parameter's gradient is marked fresh, so the first kernel that writes it this iteration
+        overwrites (beta = 0) and later passes accumulate.  Every parameter of a stepped network is written by each
+        of its backward passes; the alignment gaps between parameters stay zero for ever."""
         for p, o in zip(self.params, self.offsets):  # re-attach in case someone set .grad = None
             if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * o:
                 p.grad = self.flat_g[o:o + p.numel()].view(p.shape)
+            p._dg_fresh = True
 
     def adam(self, lr, beta1, beta2, eps, weight_decay, grad_scale):
         """Adam over the flat buffers, then refresh the bf16 GEMM copies of the conv weights in place."""

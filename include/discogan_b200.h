@@ -47,6 +47,14 @@ int dg_conv4x4s2_fprop(const void* x_big, const void* wd, void* z_small, int B, 
 /* its data gradient (cuDNN bwd-data); also nn.ConvTranspose2d(ci,co,4,2,1) forward, model.py:118-138 */
 int dg_conv4x4s2_dgrad(const void* dz_small, const void* wu, void* dx_big, int B, int Hs, int Ws, int Cs, int Cb,
                        dg_stream_t stream);
+/* forward convolutions with the BatchNorm statistics of the output fused in the epilogue: stat_part = float[2*rows*N]
+ * (rows = dg_conv_stats_rows, N = output channels) holds per-CTA partial sums / sums of squares of the fp32
+ * accumulators; finish with dg_bn_stats_finalize.  mode 0 = Conv2d fprop, 1 = ConvTranspose2d fprop. */
+int dg_conv_stats_rows(int mode, int B, int Hs, int Ws, int Cs, int Cb);
+int dg_conv4x4s2_fprop_stats(const void* x_big, const void* wd, void* z_small, float* stat_part, int B, int H, int W,
+                             int Cb, int Cs, dg_stream_t stream);
+int dg_convT4x4s2_fprop_stats(const void* x_small, const void* wu, void* y_big, float* stat_part, int B, int Hs, int Ws,
+                              int Cs, int Cb, dg_stream_t stream);
 /* same, fused with the LeakyReLU derivative of the (BN-less) layer that produced x: dx *= (mask>0 ? 1 : slope) */
 int dg_conv4x4s2_dgrad_masked(const void* dz_small, const void* wu, void* dx_big, const void* mask, float slope, int B,
                               int Hs, int Ws, int Cs, int Cb, dg_stream_t stream);
@@ -98,6 +106,9 @@ int dg_fc_wgrad(const void* small, int small_f32, const void* big, float* dw, fl
 size_t dg_bn_scratch_floats(long long P, int C);
 int dg_bn_stats(const void* z, long long P, int C, const float* gamma, const float* beta, float eps, float momentum,
                 float* stats, float* running_mean, float* running_var, float* scratch, dg_stream_t stream);
+int dg_bn_stats_finalize(const float* part, int rows, long long P, int C, const float* gamma, const float* beta,
+                         float eps, float momentum, float* stats, float* running_mean, float* running_var,
+                         dg_stream_t stream);
 int dg_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                       float eps, int C, float* stats, dg_stream_t stream);
 int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats, int act, float slope,

@@ -73,8 +73,11 @@ def test_flatnet_views():
     fn.flat_g.fill_(1.0)
     assert all(float(p.grad.sum()) == p.numel() for p in fn.params)
     net.conv1.weight.grad = None
-    fn.zero_grad()
-    assert net.conv1.weight.grad is not None and float(fn.flat_g.abs().sum()) == 0.0
+    fn.zero_grad()          # no memset: gradients are re-attached and marked fresh (first write overwrites)
+    assert net.conv1.weight.grad is not None and all(p._dg_fresh for p in fn.params)
+    buf, beta = model._grad_buf(net.conv1.weight)
+    assert beta == 0.0 and buf.data_ptr() == fn.flat_g.data_ptr()
+    assert model._grad_buf(net.conv1.weight)[1] == 1.0
 
 
 def _dp_worker(rank, world, port, out):

@@ -371,3 +371,32 @@ def test_conv_up_masked():
     _, wu = ops.pack_weights(w)
     out = ops.conv_up(to_nhwc_bf16(s.float()), wu, mask=mask, slope=0.2)
     assert rel_l2(to_nchw_f32(out), ref) < 4e-3
+
+
+@pytest.mark.parametrize("B,H,Cb,Cs", [(2, 8, 64, 128), (3, 32, 64, 128), (9, 8, 256, 512), (2, 16, 512, 1024)])
+def test_conv_fused_bn_stats(B, H, Cb, Cs):
+    """Partial sums from the GEMM epilogue -> same statistics as the stand-alone reduction over the stored output."""
+    ops = ops_mod()
+    x = rnd(B, H, H, Cb, seed=1).to(BF16)
+    w = rnd(Cs, Cb, 4, 4, seed=2) / (4 * Cb ** 0.5)
+    wd, wu = ops.pack_weights(w)
+    gamma, beta = 1 + 0.1 * rnd(Cs, seed=3), 0.1 * rnd(Cs, seed=4)
+    z, part = ops.conv_down_stats(x, wd)
+    assert torch.equal(z, ops.conv_down(x, wd))
+    P = z.numel() // Cs
+    rm, rv = torch.zeros(Cs, device="cuda"), torch.ones(Cs, device="cuda")
+    rm2, rv2 = rm.clone(), rv.clone()
+    st = ops.bn_stats_finalize(part, P, gamma, beta, rm, rv)
+    ref = ops.bn_stats(z.view(P, Cs), gamma, beta, rm2, rv2)
+    assert torch.allclose(st[0], ref[0], atol=2e-4, rtol=1e-3)           # mean (fp32 accumulators vs bf16-rounded z)
+    assert torch.allclose(st[1], ref[1], rtol=3e-3)                      # invstd
+    assert torch.allclose(rv, rv2, rtol=3e-3) and torch.allclose(rm, rm2, atol=2e-4, rtol=1e-3)
+    # transposed conv: statistics over all four output parities
+    s = rnd(B, H // 2, H // 2, Cs, seed=5).to(BF16)
+    gb, bb = 1 + 0.1 * rnd(Cb, seed=6), 0.1 * rnd(Cb, seed=7)
+    zu, partu = ops.conv_up_stats(s, wu)
+    assert torch.equal(zu, ops.conv_up(s, wu))
+    Pu = zu.numel() // Cb
+    stu = ops.bn_stats_finalize(partu, Pu, gb, bb)
+    refu = ops.bn_stats(zu.view(Pu, Cb), gb, bb)
+    assert torch.allclose(stu[0], refu[0], atol=2e-4, rtol=1e-3) and torch.allclose(stu[1], refu[1], rtol=3e-3)
