@@ -58,6 +58,54 @@ __global__ void pack_wu_kernel(const float* __restrict__ w, bf16* __restrict__ w
   for (int t = 0; t < 16; ++t) wu[((size_t)cb * 16 + t) * Cs + cs] = __float2bfloat16(v[t]);
 }
 
+// Multi-tensor version: one launch re-packs every GEMM weight of a network.  table[i] = {w, wd, wu, Cs, Cb, end}
+// (pointers as integers, `end` = running total of 2*Cs*Cb items).  First Cs*Cb items of a tensor write Wd (cb fastest),
+// the second Cs*Cb write Wu (cs fastest), so both stores stay coalesced.
+__global__ void __launch_bounds__(256)
+pack_multi_kernel(const long long* __restrict__ table, int n, long long total) {
+  __shared__ long long tb[64 * 6];
+  for (int i = threadIdx.x; i < n * 6; i += blockDim.x) tb[i] = table[i];
+  __syncthreads();
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+       it += (long long)gridDim.x * blockDim.x) {
+    int t = 0;
+    while (it >= tb[t * 6 + 5]) ++t;
+    const long long begin = t ? tb[(t - 1) * 6 + 5] : 0;
+    const float* w = reinterpret_cast<const float*>(tb[t * 6]);
+    bf16* wd = reinterpret_cast<bf16*>(tb[t * 6 + 1]);
+    bf16* wu = reinterpret_cast<bf16*>(tb[t * 6 + 2]);
+    const int Cs = (int)tb[t * 6 + 3], Cb = (int)tb[t * 6 + 4];
+    long long idx = it - begin;
+    const long long nn = (long long)Cs * Cb;
+    const bool up = idx >= nn;
+    if (up) idx -= nn;
+    int cs, cb;
+    if (!up) {
+      cb = (int)(idx % Cb);
+      cs = (int)(idx / Cb);
+      if (!wd) continue;
+    } else {
+      cs = (int)(idx % Cs);
+      cb = (int)(idx / Cs);
+      if (!wu) continue;
+    }
+    const float4* src = reinterpret_cast<const float4*>(w + ((size_t)cs * Cb + cb) * 16);
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 q = src[i];
+      v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+    if (!up) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) wd[((size_t)cs * 16 + k) * Cb + cb] = __float2bfloat16(v[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) wu[((size_t)cb * 16 + k) * Cs + cs] = __float2bfloat16(v[k]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // layout: NHWC bf16 [B][HW][C] <-> NCHW fp32 [B][C][HW], 32x32 smem tiles
 // ------------------------------------------------------------------------------------------------
@@ -702,6 +750,14 @@ int dg_pack_weights(const float* w, void* wd, void* wu, int Cs, int Cb, cudaStre
     pack_wu_kernel<<<dg_ceil_div(n, 256), 256, 0, stream>>>(w, (bf16*)wu, Cs, Cb);
     DG_CHECK_LAUNCH("pack_wu");
   }
+  return DG_OK;
+}
+
+// table: device int64 [n][6] = {w ptr, wd ptr (or 0), wu ptr (or 0), Cs, Cb, running end of 2*Cs*Cb items}; n <= 64
+int dg_pack_weights_multi(const long long* table, int n, long long total_items, cudaStream_t stream) {
+  DG_CHECK_ARG(table && n > 0 && n <= 64 && total_items > 0, "pack_weights_multi: bad args");
+  pack_multi_kernel<<<ew_grid(total_items, sms()), 256, 0, stream>>>(table, n, total_items);
+  DG_CHECK_LAUNCH("pack_weights_multi");
   return DG_OK;
 }
 

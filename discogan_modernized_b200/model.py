@@ -70,10 +70,25 @@ class _PackedWeights:
         return ent[1], ent[2]
 
     def refresh(self):
-        """Re-pack every cached weight in place from the current fp32 values."""
+        """Re-pack every cached weight in place from the current fp32 values: one multi-tensor launch for the GEMM
+        layouts plus one per image-side layer."""
+        gemm = [e for e in self._cache.values() if e[4] == "gemm"]
+        key = tuple((e[3].data_ptr(), 0 if e[1] is None else e[1].data_ptr(), 0 if e[2] is None else e[2].data_ptr())
+                    for e in gemm)
+        if gemm and getattr(self, "_table_key", None) != key:
+            rows, end = [], 0
+            for e, k in zip(gemm, key):
+                Cs, Cb = e[3].shape[0], e[3].shape[1]
+                end += 2 * Cs * Cb
+                rows.append([k[0], k[1], k[2], Cs, Cb, end])
+            self._table = torch.tensor(rows, dtype=torch.int64, device=gemm[0][3].device)
+            self._table_key, self._table_total = key, end
+        if gemm:
+            ops.pack_weights_multi(self._table, len(gemm), self._table_total)
         for ent in self._cache.values():
             p = ent[3]
-            self._pack(p, ent[4], True, True, out=(ent[1], ent[2]))
+            if ent[4] != "gemm":
+                self._pack(p, ent[4], True, True, out=(ent[1], ent[2]))
             ent[0] = (p._version, p.data_ptr())
 
     def invalidate(self):
@@ -114,6 +129,18 @@ class _BnSave:
         self.z, self.y, self.stats = z, y, stats
 
 
+def _bump_counters(mod, training):
+    """BatchNorm's num_batches_tracked: when the trainer has flattened the counters of a network into one int64
+    buffer (views keep the state-dict layout) they advance with a single add per forward; otherwise per layer.
+    Returns True if _bn_act must bump each layer's own counter."""
+    flat = getattr(mod, "_nbt_flat", None)
+    if flat is None:
+        return True
+    if training:
+        flat.add_(1)
+    return False
+
+
 def _conv_bn(conv_fn, conv_stats_fn, x, w, training):
     """Run a GEMM convolution; in training mode its epilogue also produces the partial BatchNorm sums."""
     if training and ops._conv_impl == "tc":
@@ -121,7 +148,7 @@ def _conv_bn(conv_fn, conv_stats_fn, x, w, training):
     return conv_fn(x, w), None
 
 
-def _bn_act(z, bn, act, training, part=None):
+def _bn_act(z, bn, act, training, part=None, bump=True):
     """z: NHWC bf16 (any leading dims, channels last); part: partial sums from the producing conv's epilogue.
     Returns (y, stats)."""
     C = z.shape[-1]
@@ -135,7 +162,7 @@ def _bn_act(z, bn, act, training, part=None):
             stats = ops.bn_stats_finalize(part, z2.shape[0], bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, mom)
         else:
             stats = ops.bn_stats(z2, bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, mom)
-        if rm is not None:
+        if rm is not None and bump:
             bn.num_batches_tracked.add_(1)
     else:
         stats = ops.bn_eval_stats(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
@@ -176,6 +203,7 @@ def discriminator_forward(mod, x, save=True):
     _check_input(x, mod.image_size, training)
     x = x.contiguous()
     pk = mod._packed
+    bump = _bump_counters(mod, training)
     xp = ops.img_pad_nhwc4(x)
     wc, _ = pk.get_c3(mod.conv1.weight)
     y = ops.c3_down_tc(xp, wc, ACT_LRELU, LRELU_SLOPE)
@@ -186,7 +214,7 @@ def discriminator_forward(mod, x, save=True):
         conv, bn = getattr(mod, f"conv{k}"), getattr(mod, f"bn{k}")
         wd, _ = pk.get(conv.weight, True, True)
         z, part = _conv_bn(ops.conv_down, ops.conv_down_stats, y, wd, training)
-        y, stats = _bn_act(z, bn, ACT_LRELU, training, part)
+        y, stats = _bn_act(z, bn, ACT_LRELU, training, part, bump)
         ctx.bn.append(_BnSave(z if save else None, y, stats))
         feats.append(y)
     head = getattr(mod, f"conv{mod.n_down + 1}")
@@ -319,6 +347,7 @@ def generator_forward(mod, x, save=True):
     pk = mod._packed
     enc_convs, enc_bns, head_conv, head_bn, dec_convs, dec_bns = _gen_layers(mod)
     ctx = _GenCtx()
+    bump = _bump_counters(mod, training)
     xp = ops.img_pad_nhwc4(x)
     ctx.B, ctx.xp, ctx.shape = B, (xp if save else None), x.shape
     wc, _ = pk.get_c3(enc_convs[0].weight)
@@ -327,24 +356,24 @@ def generator_forward(mod, x, save=True):
     for conv, bn in zip(enc_convs[1:], enc_bns[1:]):
         wd, _ = pk.get(conv.weight, True, True)
         z, part = _conv_bn(ops.conv_down, ops.conv_down_stats, y, wd, training)
-        y, stats = _bn_act(z, bn, ACT_LRELU, training, part)
+        y, stats = _bn_act(z, bn, ACT_LRELU, training, part, bump)
         ctx.enc.append(_BnSave(z if save else None, y, stats))
     # 4x4 valid conv to the 100-d bottleneck (model.py:107-109)
     wd, _ = pk.get(head_conv.weight, True, False)
     z = ops.fc_down(y.view(B, -1), wd.view(wd.shape[0], -1))
-    y, stats = _bn_act(z, head_bn, ACT_LRELU, training)
+    y, stats = _bn_act(z, head_bn, ACT_LRELU, training, None, bump)
     ctx.head = _BnSave(z if save else None, y, stats)
     # ConvTranspose2d(100, C, 4, 1, 0) from the 1x1 bottleneck (model.py:114-116)
     wd0, _ = pk.get(dec_convs[0].weight, True, False)
     C = wd0.shape[2]
     z = ops.fc_up(y, wd0.view(wd0.shape[0], -1)).view(B, 4, 4, C)
-    y, stats = _bn_act(z, dec_bns[0], ACT_RELU, training)
+    y, stats = _bn_act(z, dec_bns[0], ACT_RELU, training, None, bump)
     ctx.dec0 = _BnSave(z if save else None, y, stats)
     ctx.dec = []
     for conv, bn in zip(dec_convs[1:-1], dec_bns[1:]):
         _, wu = pk.get(conv.weight, True, True)
         z, part = _conv_bn(ops.conv_up, ops.conv_up_stats, y, wu, training)
-        y, stats = _bn_act(z, bn, ACT_RELU, training, part)
+        y, stats = _bn_act(z, bn, ACT_RELU, training, part, bump)
         ctx.dec.append(_BnSave(z if save else None, y, stats))
     _, wu3 = pk.get_c3(dec_convs[-1].weight)
     out = ops.c3_up_tc(y, wu3, sigmoid=True)

@@ -65,6 +65,11 @@ def pack_weights(w, want_wd=True, want_wu=True, out=None):
     return wd, wu
 
 
+def pack_weights_multi(table, n, total_items):
+    """Re-pack every (w -> wd, wu) listed in the device int64 table [n,6] with one launch."""
+    check(lib().dg_pack_weights_multi(_ptr(table, torch.int64, "table"), n, total_items, _stream()), "dg_pack_weights_multi")
+
+
 def nhwc_to_nchw_f32(x):
     B, H, W, C = x.shape
     y = torch.empty(B, C, H, W, dtype=F32, device=x.device)

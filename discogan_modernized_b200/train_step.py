@@ -58,6 +58,13 @@ class FlatNet:
             p.data = view
             p.grad = self.flat_g[o:o + p.numel()].view(p.shape)
         self.params, self.offsets = params, offs
+        # one int64 buffer for every BatchNorm counter of the network (one add per forward instead of one per layer)
+        bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d) and m.track_running_stats]
+        if bns:
+            flat = torch.stack([m.num_batches_tracked.to(dev) for m in bns]).contiguous()
+            for i, m in enumerate(bns):
+                m._buffers["num_batches_tracked"] = flat[i]
+            net._nbt_flat = flat
         net._packed.invalidate()
 
     def zero_grad(self):

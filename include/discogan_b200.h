@@ -36,6 +36,9 @@ long long dg_launch_count(void); /* kernels launched through this library so far
  * Either output may be NULL.  (Parameters: model.py:8-35,80-142.) */
 int dg_pack_weights(const float* w, void* wd, void* wu, int Cs, int Cb, dg_stream_t stream);
 
+/* all GEMM weights of a network in one launch: table = device int64 [n][6] {w, wd|0, wu|0, Cs, Cb, running end} */
+int dg_pack_weights_multi(const long long* table, int n, long long total_items, dg_stream_t stream);
+
 /* ---- layout converters for feature maps crossing the module boundary (model.py:69 returns NCHW fp32) ---- */
 int dg_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, dg_stream_t stream);
 int dg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int HW, int C, dg_stream_t stream);
