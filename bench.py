@@ -233,7 +233,7 @@ def measure_roofline(tr, batches, torch, pk):
         if name == "bn_act_fwd":
             return "bn_act_fwd", 4.0 * a[0].numel(), ""            # read z, write y (bf16)
         if name == "bn_act_bwd":
-            return "bn_act_bwd", 14.0 * a[0].numel(), ""           # reduce: dy,y,z ; dx: dy,y,z + write dz
+            return "bn_act_bwd", 10.0 * a[0].numel(), ""           # reduce: dy,z ; dx: dy,z + write dz (bf16)
         return "adam", 28.0 * a[0].numel(), ""                     # p,g,m,v read + p,m,v write (fp32); +repack excluded
 
     names = {n: conv_work for n in ("conv_down", "conv_up", "conv_wgrad", "conv_down_stats", "conv_up_stats")}

@@ -226,6 +226,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const size_t opix = ((size_t)b * p.Ho + oy) * p.Wo + ox;
       bf16* orow = p.out + opix * p.N + (size_t)t.nt * p.block_n;
       const bool valid = b < p.B;
+      // masked epilogue (always N = 64): fetch the row's 128 mask bytes before waiting for the accumulator so
+      // the DRAM latency overlaps the MMAs of this tile
+      const bool premask = p.mask != nullptr && p.block_n == 64;
+      uint4 mlo[4], mhi[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mlo[j] = mhi[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (premask && valid) {
+        const uint4* mp = reinterpret_cast<const uint4*>(p.mask + opix * p.N + (size_t)t.nt * p.block_n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          mlo[j] = mp[j];
+          mhi[j] = mp[4 + j];
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
@@ -271,7 +285,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[8 * j + e]);
               if (mrow) {
                 float m[8];
-                unpack8(*reinterpret_cast<const bf16x8*>(mrow + c + 8 * j), m);
+                if (premask) {
+                  const bool lo = c == 0;   // c is 0 or 32 here
+                  const uint32_t w0 = lo ? mlo[j].x : mhi[j].x, w1 = lo ? mlo[j].y : mhi[j].y;
+                  const uint32_t w2 = lo ? mlo[j].z : mhi[j].z, w3 = lo ? mlo[j].w : mhi[j].w;
+                  m[0] = __uint_as_float(w0 << 16); m[1] = __uint_as_float(w0 & 0xffff0000u);
+                  m[2] = __uint_as_float(w1 << 16); m[3] = __uint_as_float(w1 & 0xffff0000u);
+                  m[4] = __uint_as_float(w2 << 16); m[5] = __uint_as_float(w2 & 0xffff0000u);
+                  m[6] = __uint_as_float(w3 << 16); m[7] = __uint_as_float(w3 & 0xffff0000u);
+                } else {
+                  unpack8(*reinterpret_cast<const bf16x8*>(mrow + c + 8 * j), m);
+                }
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] *= (m[e] > 0.f ? 1.f : p.mask_slope);
               }

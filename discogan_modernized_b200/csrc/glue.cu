@@ -348,13 +348,11 @@ bn_act_fwd_kernel(const bf16* __restrict__ z, bf16* __restrict__ y, long long P,
 }
 
 // backward pass 1: per-channel sum(g) and sum(g * xhat), g = (dy [+ dy2] [+ coef*bcast]) * act'(y)
+// upstream gradient g = dy [+ dy2] [+ coef*bcast[row % bcast_rows]] (before the activation derivative)
 template <int VEC>
 __device__ __forceinline__ void bn_bwd_load_g(const bf16* dy, const bf16* dy2, const float* bcast, float coef,
-                                              long long bcast_rows, const bf16* y, long long r, int C, int c, int act,
-                                              float slope, float* g) {
-  float fy[VEC];
+                                              long long bcast_rows, long long r, int C, int c, float* g) {
   load_vec<VEC>(dy + r * C + c, g);
-  load_vec<VEC>(y + r * C + c, fy);
   if (dy2) {
     float t[VEC];
     load_vec<VEC>(dy2 + r * C + c, t);
@@ -366,55 +364,58 @@ __device__ __forceinline__ void bn_bwd_load_g(const bf16* dy, const bf16* dy2, c
 #pragma unroll
     for (int i = 0; i < VEC; ++i) g[i] += coef * bp[i];
   }
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) g[i] *= act_grad_from_out(fy[i], act, slope);
 }
 
+// backward pass 1: per-channel sum(g') and sum(g' * xhat), g' = g * act'(pre).  The activation derivative is taken from
+// the recomputed pre-activation z*scale+shift (same fp32 expression as the forward), so y is not read.
 template <int VEC>
 __global__ void __launch_bounds__(256)
 bn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const float* __restrict__ bcast,
-                      float coef, long long bcast_rows, const bf16* __restrict__ y, const bf16* __restrict__ z,
-                      const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C, int cw,
-                      int rows_iter, int rows_split, int act, float slope, float* __restrict__ part_g,
-                      float* __restrict__ part_gx) {
+                      float coef, long long bcast_rows, const bf16* __restrict__ z, const float* __restrict__ stats,
+                      long long P, int C, int cw, int rows_iter, int rows_split, int act, float slope,
+                      float* __restrict__ part_g, float* __restrict__ part_gx) {
   const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
   const int c = (blockIdx.x * cw + tx) * VEC;
   float s1[VEC], s2[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) s1[i] = s2[i] = 0.f;
   if (c < C) {
-    float mu[VEC], is[VEC];
+    float mu[VEC], is[VEC], sc[VEC], sh[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      mu[i] = mean[c + i];
-      is[i] = invstd[c + i];
+      mu[i] = stats[c + i];
+      is[i] = stats[C + c + i];
+      sc[i] = stats[2 * C + c + i];
+      sh[i] = stats[3 * C + c + i];
     }
     const long long r0 = (long long)blockIdx.y * rows_split;
     const long long r1 = min(P, r0 + rows_split);
     long long r = r0 + ty;
-    for (; r + rows_iter < r1; r += 2LL * rows_iter) {   // two rows (6 independent loads) in flight
-      float g[2][VEC], fz[2][VEC];
+    for (; r + 3LL * rows_iter < r1; r += 4LL * rows_iter) {   // four rows (8 independent 16-byte loads) in flight
+      float g[4][VEC], fz[4][VEC];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, y, r + (long long)u * rows_iter, C, c, act, slope, g[u]);
+      for (int u = 0; u < 4; ++u) {
+        bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, r + (long long)u * rows_iter, C, c, g[u]);
         load_vec<VEC>(z + (r + (long long)u * rows_iter) * C + c, fz[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          s1[i] += g[u][i];
-          s2[i] += g[u][i] * (fz[u][i] - mu[i]) * is[i];
+          const float gg = g[u][i] * act_grad_from_out(fz[u][i] * sc[i] + sh[i], act, slope);
+          s1[i] += gg;
+          s2[i] += gg * (fz[u][i] - mu[i]) * is[i];
         }
     }
     for (; r < r1; r += rows_iter) {
       float g[VEC], fz[VEC];
-      bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, y, r, C, c, act, slope, g);
+      bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, r, C, c, g);
       load_vec<VEC>(z + r * C + c, fz);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        s1[i] += g[i];
-        s2[i] += g[i] * (fz[i] - mu[i]) * is[i];
+        const float gg = g[i] * act_grad_from_out(fz[i] * sc[i] + sh[i], act, slope);
+        s1[i] += gg;
+        s2[i] += gg * (fz[i] - mu[i]) * is[i];
       }
     }
   }
@@ -457,17 +458,19 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part_g, const f
 template <int VEC>
 __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const float* __restrict__ bcast, float coef,
-                 long long bcast_rows, const bf16* __restrict__ y, const bf16* __restrict__ z,
-                 const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coefs,
-                 bf16* __restrict__ dz, long long P, int C, int cw, int rows_iter, int rows_split, int act, float slope) {
+                 long long bcast_rows, const bf16* __restrict__ z, const float* __restrict__ stats,
+                 const float* __restrict__ coefs, bf16* __restrict__ dz, long long P, int C, int cw, int rows_iter,
+                 int rows_split, int act, float slope) {
   const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
   const int c = (blockIdx.x * cw + tx) * VEC;
   if (c >= C) return;
-  float mu[VEC], is[VEC], k0[VEC], k1[VEC], k2[VEC];
+  float mu[VEC], is[VEC], sc[VEC], sh[VEC], k0[VEC], k1[VEC], k2[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    mu[i] = mean[c + i];
-    is[i] = invstd[c + i];
+    mu[i] = stats[c + i];
+    is[i] = stats[C + c + i];
+    sc[i] = stats[2 * C + c + i];
+    sh[i] = stats[3 * C + c + i];
     k0[i] = coefs[c + i];
     k1[i] = coefs[C + c + i];
     k2[i] = coefs[2 * C + c + i];
@@ -475,26 +478,32 @@ bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, cons
   const long long r0 = (long long)blockIdx.y * rows_split;
   const long long r1 = min(P, r0 + rows_split);
   long long r = r0 + ty;
-  for (; r + rows_iter < r1; r += 2LL * rows_iter) {
-    float g[2][VEC], fz[2][VEC];
+  for (; r + 3LL * rows_iter < r1; r += 4LL * rows_iter) {
+    float g[4][VEC], fz[4][VEC];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, y, r + (long long)u * rows_iter, C, c, act, slope, g[u]);
+    for (int u = 0; u < 4; ++u) {
+      bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, r + (long long)u * rows_iter, C, c, g[u]);
       load_vec<VEC>(z + (r + (long long)u * rows_iter) * C + c, fz[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 4; ++u) {
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) g[u][k] = k0[k] * (g[u][k] - k1[k] - (fz[u][k] - mu[k]) * is[k] * k2[k]);
+      for (int k = 0; k < VEC; ++k) {
+        const float gg = g[u][k] * act_grad_from_out(fz[u][k] * sc[k] + sh[k], act, slope);
+        g[u][k] = k0[k] * (gg - k1[k] - (fz[u][k] - mu[k]) * is[k] * k2[k]);
+      }
       store_vec<VEC>(dz + (r + (long long)u * rows_iter) * C + c, g[u]);
     }
   }
   for (; r < r1; r += rows_iter) {
     float g[VEC], fz[VEC];
-    bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, y, r, C, c, act, slope, g);
+    bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, r, C, c, g);
     load_vec<VEC>(z + r * C + c, fz);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) g[k] = k0[k] * (g[k] - k1[k] - (fz[k] - mu[k]) * is[k] * k2[k]);
+    for (int k = 0; k < VEC; ++k) {
+      const float gg = g[k] * act_grad_from_out(fz[k] * sc[k] + sh[k], act, slope);
+      g[k] = k0[k] * (gg - k1[k] - (fz[k] - mu[k]) * is[k] * k2[k]);
+    }
     store_vec<VEC>(dz + r * C + c, g);
   }
 }
@@ -851,37 +860,37 @@ int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bca
                   const void* y, const void* z, const float* stats, const float* gamma, long long P, int C, int act,
                   float slope, float* dgamma, float* dbeta, float grad_beta, void* dz, float* coefs, float* scratch,
                   cudaStream_t stream) {
-  DG_CHECK_ARG(P > 0 && C > 0 && dy && y && z && stats && dz && coefs && scratch, "bn_act_bwd: bad args");
+  (void)y;  // the activation derivative is recomputed from z and the statistics; y is accepted for API symmetry
+  DG_CHECK_ARG(P > 0 && C > 0 && dy && z && stats && dz && coefs && scratch, "bn_act_bwd: bad args");
   DG_CHECK_ARG(!bcast || bcast_rows > 0, "bn_act_bwd: bcast_rows must be positive");
   const int vec = (C % 8 == 0) ? 8 : 1;
   BnGeom g = bn_geom(P, C, vec, sms());
   float* pg = scratch;
   float* pgx = scratch + (size_t)g.gy * C;
   dim3 grid(g.gx, g.gy);
-  const float* mean = stats;
   const float* invstd = stats + C;
   if (vec == 8)
     bn_bwd_partial_kernel<8><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
-                                                       (const bf16*)y, (const bf16*)z, mean, invstd, P, C, g.cw,
-                                                       g.rows_iter, g.rows_split, act, slope, pg, pgx);
+                                                       (const bf16*)z, stats, P, C, g.cw, g.rows_iter, g.rows_split, act,
+                                                       slope, pg, pgx);
   else
     bn_bwd_partial_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
-                                                       (const bf16*)y, (const bf16*)z, mean, invstd, P, C, g.cw,
-                                                       g.rows_iter, g.rows_split, act, slope, pg, pgx);
+                                                       (const bf16*)z, stats, P, C, g.cw, g.rows_iter, g.rows_split, act,
+                                                       slope, pg, pgx);
   DG_CHECK_LAUNCH("bn_bwd_partial");
   bn_bwd_finalize_kernel<<<dg_ceil_div(C, 32), 256, 0, stream>>>(pg, pgx, g.gy, P, C, gamma, invstd, dgamma, dbeta,
-                                                                  grad_beta, coefs);
+                                                                 grad_beta, coefs);
   DG_CHECK_LAUNCH("bn_bwd_finalize");
   BnGeom g2 = bn_geom(P, C, vec, sms(), 8);
   dim3 grid2(g2.gx, g2.gy);
   if (vec == 8)
     bn_bwd_dx_kernel<8><<<grid2, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
-                                                   (const bf16*)y, (const bf16*)z, mean, invstd, coefs, (bf16*)dz, P, C,
-                                                   g2.cw, g2.rows_iter, g2.rows_split, act, slope);
+                                                   (const bf16*)z, stats, coefs, (bf16*)dz, P, C, g2.cw, g2.rows_iter,
+                                                   g2.rows_split, act, slope);
   else
     bn_bwd_dx_kernel<1><<<grid2, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
-                                                   (const bf16*)y, (const bf16*)z, mean, invstd, coefs, (bf16*)dz, P, C,
-                                                   g2.cw, g2.rows_iter, g2.rows_split, act, slope);
+                                                   (const bf16*)z, stats, coefs, (bf16*)dz, P, C, g2.cw, g2.rows_iter,
+                                                   g2.rows_split, act, slope);
   DG_CHECK_LAUNCH("bn_bwd_dx");
   return DG_OK;
 }

@@ -14,6 +14,7 @@ of the depth-parametrised family: ``n_down = log2(S) - 2`` stride-2 layers with 
 ``64 * 2**min(i, 5)``.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -22,6 +23,7 @@ from . import ops
 from .ops import ACT_LRELU, ACT_RELU
 
 LRELU_SLOPE = 0.2
+_FUSE_BN_STATS = os.environ.get("DISCOGAN_B200_FUSE_STATS", "1") != "0"   # debugging switch
 
 
 def family_channels(image_size: int):
@@ -143,7 +145,7 @@ def _bump_counters(mod, training):
 
 def _conv_bn(conv_fn, conv_stats_fn, x, w, training):
     """Run a GEMM convolution; in training mode its epilogue also produces the partial BatchNorm sums."""
-    if training and ops._conv_impl == "tc":
+    if training and ops._conv_impl == "tc" and _FUSE_BN_STATS:
         return conv_stats_fn(x, w)
     return conv_fn(x, w), None
 
