@@ -369,7 +369,7 @@ __device__ __forceinline__ void bn_bwd_load_g(const bf16* dy, const bf16* dy2, c
 // backward pass 1: per-channel sum(g') and sum(g' * xhat), g' = g * act'(pre).  The activation derivative is taken from
 // the recomputed pre-activation z*scale+shift (same fp32 expression as the forward), so y is not read.
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const float* __restrict__ bcast,
                       float coef, long long bcast_rows, const bf16* __restrict__ z, const float* __restrict__ stats,
                       long long P, int C, int cw, int rows_iter, int rows_split, int act, float slope,
@@ -380,31 +380,30 @@ bn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2,
 #pragma unroll
   for (int i = 0; i < VEC; ++i) s1[i] = s2[i] = 0.f;
   if (c < C) {
-    float mu[VEC], is[VEC], sc[VEC], sh[VEC];
+    float mu[VEC], sc[VEC], sh[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       mu[i] = stats[c + i];
-      is[i] = stats[C + c + i];
       sc[i] = stats[2 * C + c + i];
       sh[i] = stats[3 * C + c + i];
     }
     const long long r0 = (long long)blockIdx.y * rows_split;
     const long long r1 = min(P, r0 + rows_split);
     long long r = r0 + ty;
-    for (; r + 3LL * rows_iter < r1; r += 4LL * rows_iter) {   // four rows (8 independent 16-byte loads) in flight
-      float g[4][VEC], fz[4][VEC];
+    for (; r + rows_iter < r1; r += 2LL * rows_iter) {   // two rows (4+ independent 16-byte loads) in flight
+      float g[2][VEC], fz[2][VEC];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, r + (long long)u * rows_iter, C, c, g[u]);
         load_vec<VEC>(z + (r + (long long)u * rows_iter) * C + c, fz[u]);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
           const float gg = g[u][i] * act_grad_from_out(fz[u][i] * sc[i] + sh[i], act, slope);
           s1[i] += gg;
-          s2[i] += gg * (fz[u][i] - mu[i]) * is[i];
+          s2[i] += gg * (fz[u][i] - mu[i]);
         }
     }
     for (; r < r1; r += rows_iter) {
@@ -415,9 +414,11 @@ bn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2,
       for (int i = 0; i < VEC; ++i) {
         const float gg = g[i] * act_grad_from_out(fz[i] * sc[i] + sh[i], act, slope);
         s1[i] += gg;
-        s2[i] += gg * (fz[i] - mu[i]) * is[i];
+        s2[i] += gg * (fz[i] - mu[i]);
       }
     }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s2[i] *= stats[C + c + i];   // xhat = (z - mean) * invstd
   }
   bn_block_reduce_store<VEC>(s1, s2, cw, rows_iter, tx, ty, c, C, part_g, part_gx, blockIdx.y);
 }
@@ -456,7 +457,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part_g, const f
 
 // backward pass 2: dz = gamma*invstd * (g - mean(g) - xhat * mean(g*xhat))
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const float* __restrict__ bcast, float coef,
                  long long bcast_rows, const bf16* __restrict__ z, const float* __restrict__ stats,
                  const float* __restrict__ coefs, bf16* __restrict__ dz, long long P, int C, int cw, int rows_iter,
@@ -464,33 +465,34 @@ bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, cons
   const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
   const int c = (blockIdx.x * cw + tx) * VEC;
   if (c >= C) return;
-  float mu[VEC], is[VEC], sc[VEC], sh[VEC], k0[VEC], k1[VEC], k2[VEC];
+  // dz = k0*(g' - k1 - (z-mu)*is*k2) = k0*g' + a1*z + a0
+  float sc[VEC], sh[VEC], k0[VEC], a1[VEC], a0[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    mu[i] = stats[c + i];
-    is[i] = stats[C + c + i];
+    const float mu = stats[c + i], is = stats[C + c + i];
     sc[i] = stats[2 * C + c + i];
     sh[i] = stats[3 * C + c + i];
     k0[i] = coefs[c + i];
-    k1[i] = coefs[C + c + i];
-    k2[i] = coefs[2 * C + c + i];
+    const float k1 = coefs[C + c + i], k2 = coefs[2 * C + c + i];
+    a1[i] = -k0[i] * k2 * is;
+    a0[i] = -k0[i] * k1 - a1[i] * mu;
   }
   const long long r0 = (long long)blockIdx.y * rows_split;
   const long long r1 = min(P, r0 + rows_split);
   long long r = r0 + ty;
-  for (; r + 3LL * rows_iter < r1; r += 4LL * rows_iter) {
-    float g[4][VEC], fz[4][VEC];
+  for (; r + rows_iter < r1; r += 2LL * rows_iter) {
+    float g[2][VEC], fz[2][VEC];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
       bn_bwd_load_g<VEC>(dy, dy2, bcast, coef, bcast_rows, r + (long long)u * rows_iter, C, c, g[u]);
       load_vec<VEC>(z + (r + (long long)u * rows_iter) * C + c, fz[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
         const float gg = g[u][k] * act_grad_from_out(fz[u][k] * sc[k] + sh[k], act, slope);
-        g[u][k] = k0[k] * (gg - k1[k] - (fz[u][k] - mu[k]) * is[k] * k2[k]);
+        g[u][k] = k0[k] * gg + a1[k] * fz[u][k] + a0[k];
       }
       store_vec<VEC>(dz + (r + (long long)u * rows_iter) * C + c, g[u]);
     }
@@ -502,7 +504,7 @@ bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, cons
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const float gg = g[k] * act_grad_from_out(fz[k] * sc[k] + sh[k], act, slope);
-      g[k] = k0[k] * (gg - k1[k] - (fz[k] - mu[k]) * is[k] * k2[k]);
+      g[k] = k0[k] * gg + a1[k] * fz[k] + a0[k];
     }
     store_vec<VEC>(dz + r * C + c, g);
   }

@@ -91,8 +91,8 @@ class GradReducer:
     """Average flat gradient buffers over the data-parallel group.  CUDA: NCCL all-reduce on a side
     stream ordered after the producing kernels, joined before Adam.  CPU tensors (gloo, tests): blocking."""
 
-    def __init__(self, group=None):
-        self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    def __init__(self, group=None, enabled=True):
+        self.enabled = enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.group = group
         self.world = dist.get_world_size(group) if self.enabled else 1
         self._stream = None
@@ -159,7 +159,7 @@ class DiscoGANTrainer:
     def __init__(self, image_size=512, device="cuda", model_arch="discogan", learning_rate=2e-4, beta1=0.5,
                  beta2=0.999, weight_decay=1e-5, update_interval=3, gan_curriculum=10000, starting_rate=None,
                  default_rate=None, variant="image_translation", seed=None, nets=None, process_group=None,
-                 use_graphs=None):
+                 use_graphs=None, data_parallel=True):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("DiscoGANTrainer runs on CUDA (sm_100a) only")
@@ -182,7 +182,7 @@ class DiscoGANTrainer:
                     Discriminator(image_size=image_size), Discriminator(image_size=image_size)]
         self.G_A, self.G_B, self.D_A, self.D_B = [n.to(self.device).train() for n in nets]
         self.flat = {n: FlatNet(n) for n in (self.G_A, self.G_B, self.D_A, self.D_B)}
-        self.reducer = GradReducer(process_group)
+        self.reducer = GradReducer(process_group, enabled=data_parallel)
         self.reducer.broadcast_params(self.flat.values())
         self.loss_buf = torch.zeros(len(LOSS_NAMES), dtype=torch.float32, device=self.device)
         self.iters = 0

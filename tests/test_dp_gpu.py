@@ -1,0 +1,69 @@
+"""Data-parallel step on >= 2 GPUs (NCCL): skipped on single-GPU boxes; the host-side reducer logic is covered on
+CPU with gloo in tests/test_host_logic.py."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, same_batch, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from discogan_modernized_b200 import DiscoGANTrainer
+    from oracle.step import synthetic_batch
+    S, B, steps = 64, 8, 5
+    torch.manual_seed(100 + rank)                      # different init per rank: the trainer must broadcast rank 0's
+    tr = DiscoGANTrainer(image_size=S, device=f"cuda:{rank}")
+    for it in range(steps):
+        A, Bt = synthetic_batch(B, S, step=it, rank=0 if same_batch else rank, device=f"cuda:{rank}")
+        tr.step(A, Bt)
+    torch.cuda.synchronize()
+    flat = torch.cat([tr.flat[n].flat_p for n in tr.nets()])
+    gathered = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    rm = tr.G_A.encoder[3].running_mean.clone()
+    rms = [torch.empty_like(rm) for _ in range(world)]
+    dist.all_gather(rms, rm)
+    if rank == 0:
+        res = {"sync": all(torch.equal(gathered[0], g) for g in gathered[1:]),
+               "bn_equal": all(torch.allclose(rms[0], r, rtol=1e-4, atol=1e-6) for r in rms[1:]),
+               "losses": tr.losses()}
+        if same_batch:                                  # identical shards => identical to single-GPU training
+            torch.manual_seed(100)
+            single = DiscoGANTrainer(image_size=S, device="cuda:0", data_parallel=False)
+            for it in range(steps):
+                A, Bt = synthetic_batch(B, S, step=it, rank=0, device="cuda:0")
+                single.step(A, Bt)
+            ref = torch.cat([single.flat[n].flat_p for n in single.nets()])
+            res["max_diff_vs_single"] = float((ref - flat).abs().max())
+            res["mean_diff_vs_single"] = float((ref - flat).abs().mean())
+            res["single_losses"] = single.losses()
+        out.update(res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("same_batch", [True, False])
+def test_data_parallel_step(same_batch):
+    world, port = 2, 29541 + int(same_batch)
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, same_batch, out), nprocs=world, join=True)
+        out = dict(out)
+    assert out["sync"], "weights diverged across ranks"
+    if same_batch:
+        assert out["bn_equal"]
+        # same data on both ranks: averaged gradients equal the single-GPU gradients (up to the fp32 summation order
+        # of the fused BatchNorm statistics), so five Adam steps land on the same weights
+        assert out["max_diff_vs_single"] < 2.1e-3, out["max_diff_vs_single"]      # <= 2 * steps * lr (a flipped sign)
+        assert out["mean_diff_vs_single"] < 2e-5, out["mean_diff_vs_single"]
+        for k, v in out["single_losses"].items():
+            assert abs(out["losses"][k] - v) <= 0.02 * abs(v) + 5e-3, (k, out["losses"][k], v)
+    else:
+        assert not out["bn_equal"], "BatchNorm statistics must stay per rank"
