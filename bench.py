@@ -367,9 +367,18 @@ def run_b200(args, S, B):
             v, msc, cores, sample, _ = cpu_reference_pairs_per_s(S, B, 3, 1, args.model_arch, budget_s=60.0)
             line["cpu_baseline"] = {"value": v, "unit": "image-pairs/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # release the captured graphs before leaving; skip destroy_process_group (an NCCL communicator that was
+        # captured into CUDA graphs can block in teardown) -- exiting the process is the documented alternative
+        try:
+            tr.close()
+        except NameError:
+            pass
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

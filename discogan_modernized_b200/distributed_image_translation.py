@@ -35,11 +35,15 @@ def main(argv=None):
         args.world_size = int(os.environ.get("WORLD_SIZE", args.world_size))
     if args.distributed:
         setup(args.local_rank, args.world_size)
+    tr = None
     try:
-        return run_training(args, "distributed", rank=args.local_rank if args.distributed else 0,
-                            world=args.world_size if args.distributed else 1)
+        tr = run_training(args, "distributed", rank=args.local_rank if args.distributed else 0,
+                          world=args.world_size if args.distributed else 1)
+        return tr
     finally:
         if args.distributed:
+            if tr is not None:
+                tr.close()           # captured graphs must go before the NCCL communicator
             dist.barrier()
             cleanup()
 

@@ -351,3 +351,14 @@ class DiscoGANTrainer:
 
     def nets(self):
         return self.G_A, self.G_B, self.D_A, self.D_B
+
+    def close(self):
+        """Drop the captured CUDA graphs and their memory pool.  Call before ``dist.destroy_process_group()``: NCCL
+        cannot tear down a communicator while instantiated graphs still reference its kernels."""
+        torch.cuda.synchronize()
+        self._graphs.clear()
+        self._graph_launches.clear()
+        self._eager_done.clear()
+        self._static.clear()
+        self._pool = None
+        torch.cuda.synchronize()

@@ -43,9 +43,12 @@ def _worker(rank, world, port, same_batch, out):
             res["max_diff_vs_single"] = float((ref - flat).abs().max())
             res["mean_diff_vs_single"] = float((ref - flat).abs().mean())
             res["single_losses"] = single.losses()
+            single.close()
         out.update(res)
+    tr.close()                       # graphs first: NCCL teardown blocks while captured graphs reference the communicator
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
