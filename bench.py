@@ -287,9 +287,16 @@ def measure_roofline(tr, batches, torch, pk):
                      for k, (a, sec, n) in top}
     g = by.get("conv_gemm", [0.0, 1.0, 1])
     ach = g[0] / g[1] / 1e12
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel (profiles/README.md); only the
+    # 512^2 B=32 workload has been captured so far
+    traffic = None
+    tfile = ROOT / "profiles" / "ncu_traffic.json"
+    big = batches[0][0]
+    if tfile.exists() and big.shape[-1] == 512 and big.shape[0] == 32:
+        traffic = json.loads(tfile.read_text())["conv_gemm_kernel"]["dram_bytes_per_launch"]
     roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: conv fprop/dgrad, convT fprop/dgrad)",
             "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-            "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside the step)", "traffic": None,
+            "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside the step)", "traffic": traffic,
             "launches_per_cycle": g[2], "avg_launch_us": g[1] / max(g[2], 1) * 1e6,
             "algorithmic": "2*B*Ho*Wo*Co*Ci*16 FLOP per launch"}
     return roof, out
