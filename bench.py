@@ -217,11 +217,11 @@ def measure_roofline(tr, batches, torch, pk):
     recs = []
 
     def conv_work(name, a):
-        if name in ("conv_down", "conv_down_bn"):
+        if name in ("conv_down", "conv_down_stats"):
             big, wd = a[0], a[1]
             return "conv_gemm", conv_flops(big.shape[0], big.shape[1] // 2, wd.shape[0], big.shape[3]), \
                 f"down B{big.shape[0]} {big.shape[1]}->{big.shape[1] // 2} {big.shape[3]}->{wd.shape[0]}"
-        if name in ("conv_up", "conv_up_bn"):
+        if name in ("conv_up", "conv_up_stats"):
             small, wu = a[0], a[1]
             return "conv_gemm", conv_flops(small.shape[0], small.shape[1], small.shape[3], wu.shape[0]), \
                 f"up B{small.shape[0]} {small.shape[1]}->{2 * small.shape[1]} {small.shape[3]}->{wu.shape[0]}"
@@ -236,7 +236,7 @@ def measure_roofline(tr, batches, torch, pk):
             return "bn_act_bwd", 10.0 * a[0].numel(), ""           # reduce: dy,z ; dx: dy,z + write dz (bf16)
         return "adam", 28.0 * a[0].numel(), ""                     # p,g,m,v read + p,m,v write (fp32); +repack excluded
 
-    names = {n: conv_work for n in ("conv_down", "conv_up", "conv_wgrad", "conv_down_bn", "conv_up_bn")}
+    names = {n: conv_work for n in ("conv_down", "conv_up", "conv_wgrad", "conv_down_stats", "conv_up_stats")}
     names.update({n: hbm_work for n in ("bn_act_fwd", "bn_act_bwd", "adam_step")})
     orig = {n: getattr(ops, n) for n in names}
 

@@ -32,21 +32,6 @@ constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;           // TMEM columns between the two accumulator stages
 constexpr int kMaxStages = 8;
 
-// BatchNorm statistics finished inside the GEMM kernel: every CTA adds its per-channel sums to `acc` (float[2N],
-// zero on entry), the last CTA to arrive turns them into mean / invstd / scale / shift, updates the running
-// statistics and leaves `acc` and `counter` zeroed for the next launch.
-struct BnFuse {
-  float* acc;
-  int* counter;
-  const float* gamma;
-  const float* beta;
-  float eps, momentum;
-  float* stats;  // [4N] = mean, invstd, scale, shift
-  float* running_mean;
-  float* running_var;
-  long long P;   // elements per channel
-};
-
 struct ConvGemmParams {
   int mode;  // 0 = DOWN, 1 = UP
   int B, Hm, Wm;  // M-side (small tensor) spatial dims
@@ -68,7 +53,6 @@ struct ConvGemmParams {
   int img_sigmoid, img_accumulate;
   float* stat_part;   // BatchNorm statistics fused in the epilogue: per-CTA partial sums [2][gridDim.x][N] of the fp32
                       // accumulators (sum, sum of squares) over the rows this CTA produced; NULL = off
-  BnFuse bn;          // bn.acc != NULL: finish the statistics in this kernel (last-CTA pattern)
 };
 
 // Sum the 32 values each lane holds for 32 columns over the 32 lanes (rows) of the warp: afterwards v[0] of lane l is
@@ -221,8 +205,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool want_stats = p.stat_part != nullptr || p.bn.acc != nullptr;
-    if (want_stats) {
+    if (p.stat_part) {
       for (int i = threadIdx.x - 64; i < 2 * p.N; i += 128) s_stat[i] = 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
@@ -282,7 +265,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           tmem_ld_32x32(taddr + c, r);
           tmem_ld_wait();
-          if (want_stats) {   // rows beyond the batch are exact zeros (TMA zero fill), so no masking is needed
+          if (p.stat_part) {   // rows beyond the batch are exact zeros (TMA zero fill), so no masking is needed
             float v[32];
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
@@ -334,44 +317,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = threadIdx.x - 64; i < p.N; i += 128) {
         ps[i] = s_stat[i];
         pq[i] = s_stat[p.N + i];
-      }
-    }
-    if (p.bn.acc) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < 2 * p.N; i += 128) atomicAdd(&p.bn.acc[i], s_stat[i]);
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
-      if (threadIdx.x == 64) {
-        const int prev = atomicAdd(p.bn.counter, 1);
-        const int last = prev == (int)gridDim.x - 1;
-        if (last) *p.bn.counter = 0;
-        *s_flag = last;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*s_flag) {
-        __threadfence();
-        const double invP = 1.0 / (double)p.bn.P;
-        for (int c = threadIdx.x - 64; c < p.N; c += 128) {
-          const double sum = (double)__ldcg(&p.bn.acc[c]);
-          const double sq = (double)__ldcg(&p.bn.acc[p.N + c]);
-          p.bn.acc[c] = 0.f;
-          p.bn.acc[p.N + c] = 0.f;
-          const double m = sum * invP;
-          double var = sq * invP - m * m;
-          if (var < 0.0) var = 0.0;
-          const float is = (float)(1.0 / sqrt(var + (double)p.bn.eps));
-          const float sc = p.bn.gamma[c] * is;
-          p.bn.stats[c] = (float)m;
-          p.bn.stats[p.N + c] = is;
-          p.bn.stats[2 * p.N + c] = sc;
-          p.bn.stats[3 * p.N + c] = p.bn.beta[c] - (float)m * sc;
-          if (p.bn.running_mean) {
-            const double unbiased = p.bn.P > 1 ? var * (double)p.bn.P / (double)(p.bn.P - 1) : var;
-            p.bn.running_mean[c] = (1.f - p.bn.momentum) * p.bn.running_mean[c] + p.bn.momentum * (float)m;
-            p.bn.running_var[c] = (1.f - p.bn.momentum) * p.bn.running_var[c] + p.bn.momentum * (float)unbiased;
-          }
-        }
       }
     }
   }
@@ -603,7 +548,6 @@ struct ConvGemmExtras {
   int img_sigmoid = 0, img_accumulate = 0;
   float* stat_part = nullptr;  // [2][grid][N] partial BatchNorm sums
   int* grid_out = nullptr;     // plan query: receives the grid size, nothing is launched
-  BnFuse bn = {nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, nullptr, 0};
 };
 
 int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, int B, int Hs, int Ws, int Cs, int Cb,
@@ -650,8 +594,6 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   p.img_sigmoid = ex.img_sigmoid;
   p.img_accumulate = ex.img_accumulate;
   p.stat_part = ex.stat_part;
-  p.bn = ex.bn;
-  p.bn.P = (long long)B * p.Ho * p.Wo;
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   if (ex.grid_out) {
     *ex.grid_out = grid;
@@ -661,7 +603,7 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   int stages = (200 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
-  const int smem_bytes = stages * stage_bytes + 1024 + 256 + ((ex.stat_part || ex.bn.acc) ? 2 * N * (int)sizeof(float) : 0);
+  const int smem_bytes = stages * stage_bytes + 1024 + 256 + (ex.stat_part ? 2 * N * (int)sizeof(float) : 0);
   DG_CHECK_ARG(smem_bytes <= 227 * 1024, "conv gemm: N=%d too wide for fused statistics", N);
 
   CUtensorMap tmA, tmB;
@@ -750,27 +692,6 @@ int dg_convT4x4s2_fprop_stats(const void* x_small, const void* wu, void* y_big, 
   ConvGemmExtras ex;
   ex.stat_part = stat_part;
   return launch_conv_gemm(1, x_small, wu, y_big, B, Hs, Ws, Cs, Cb, stream, ex);
-}
-
-// Forward convolution + complete training-mode BatchNorm statistics of its output in ONE launch.
-// mode 0: Conv2d fprop (x = big [B,2Hs,2Ws,Cb] -> z = small), mode 1: ConvTranspose2d fprop (x = small -> z = big).
-// acc: float[2*N] zeroed once by the caller (N = output channels), counter: int zeroed once; both are left zeroed.
-// stats: float[4*N] {mean, invstd, scale, shift}; running_* may be NULL.
-int dg_conv4x4s2_fprop_bn(int mode, const void* x, const void* w_packed, void* z, int B, int Hs, int Ws, int Cs, int Cb,
-                          const float* gamma, const float* beta, float eps, float momentum, float* stats,
-                          float* running_mean, float* running_var, float* acc, int* counter, cudaStream_t stream) {
-  DG_CHECK_ARG((mode == 0 || mode == 1) && gamma && beta && stats && acc && counter, "fprop_bn: bad args");
-  ConvGemmExtras ex;
-  ex.bn.acc = acc;
-  ex.bn.counter = counter;
-  ex.bn.gamma = gamma;
-  ex.bn.beta = beta;
-  ex.bn.eps = eps;
-  ex.bn.momentum = momentum;
-  ex.bn.stats = stats;
-  ex.bn.running_mean = running_mean;
-  ex.bn.running_var = running_var;
-  return launch_conv_gemm(mode, x, w_packed, z, B, Hs, Ws, Cs, Cb, stream, ex);
 }
 
 // dgrad whose consumer is a BN-less LeakyReLU layer: dx = dgrad * (mask > 0 ? 1 : slope), mask = that layer's output

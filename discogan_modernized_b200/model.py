@@ -143,28 +143,16 @@ def _bump_counters(mod, training):
     return False
 
 
-def _conv_bn_act(kind, x, w, bn, act, training, bump):
-    """GEMM convolution ('down' = Conv2d, 'up' = ConvTranspose2d) -> BatchNorm -> activation.  In training mode the
-    convolution kernel also produces the batch statistics (and the running-stat update) in its last CTA.
-    Returns (z, y, stats)."""
-    conv = ops.conv_down if kind == "down" else ops.conv_up
-    if training and bn.track_running_stats and ops._conv_impl == "tc" and _FUSE_BN_STATS:
-        fused = ops.conv_down_bn if kind == "down" else ops.conv_up_bn
-        z, stats = fused(x, w, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps,
-                         bn.momentum if bn.momentum is not None else 0.1)
-        if z.numel() // z.shape[-1] < 2:
-            raise ValueError("Expected more than 1 value per channel when training")
-        if bump:
-            bn.num_batches_tracked.add_(1)
-        y = ops.bn_act_fwd(z.view(-1, z.shape[-1]), stats, act, LRELU_SLOPE).view(z.shape)
-        return z, y, stats
-    z = conv(x, w)
-    y, stats = _bn_act(z, bn, act, training, None, bump)
-    return z, y, stats
+def _conv_bn(conv_fn, conv_stats_fn, x, w, training):
+    """Run a GEMM convolution; in training mode its epilogue also produces the partial BatchNorm sums."""
+    if training and ops._conv_impl == "tc" and _FUSE_BN_STATS:
+        return conv_stats_fn(x, w)
+    return conv_fn(x, w), None
 
 
 def _bn_act(z, bn, act, training, part=None, bump=True):
-    """z: NHWC bf16 (any leading dims, channels last).  Returns (y, stats)."""
+    """z: NHWC bf16 (any leading dims, channels last); part: partial sums from the producing conv's epilogue.
+    Returns (y, stats)."""
     C = z.shape[-1]
     z2 = z.view(-1, C)
     if training or not bn.track_running_stats:
@@ -172,7 +160,10 @@ def _bn_act(z, bn, act, training, part=None, bump=True):
             raise ValueError("Expected more than 1 value per channel when training")
         rm, rv = (bn.running_mean, bn.running_var) if (training and bn.track_running_stats) else (None, None)
         mom = bn.momentum if bn.momentum is not None else 0.1
-        stats = ops.bn_stats(z2, bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, mom)
+        if part is not None:
+            stats = ops.bn_stats_finalize(part, z2.shape[0], bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, mom)
+        else:
+            stats = ops.bn_stats(z2, bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, mom)
         if rm is not None and bump:
             bn.num_batches_tracked.add_(1)
     else:
@@ -224,7 +215,8 @@ def discriminator_forward(mod, x, save=True):
     for k in range(2, mod.n_down + 1):
         conv, bn = getattr(mod, f"conv{k}"), getattr(mod, f"bn{k}")
         wd, _ = pk.get(conv.weight, True, True)
-        z, y, stats = _conv_bn_act("down", y, wd, bn, ACT_LRELU, training, bump)
+        z, part = _conv_bn(ops.conv_down, ops.conv_down_stats, y, wd, training)
+        y, stats = _bn_act(z, bn, ACT_LRELU, training, part, bump)
         ctx.bn.append(_BnSave(z if save else None, y, stats))
         feats.append(y)
     head = getattr(mod, f"conv{mod.n_down + 1}")
@@ -365,7 +357,8 @@ def generator_forward(mod, x, save=True):
     ctx.y1, ctx.enc = y, []
     for conv, bn in zip(enc_convs[1:], enc_bns[1:]):
         wd, _ = pk.get(conv.weight, True, True)
-        z, y, stats = _conv_bn_act("down", y, wd, bn, ACT_LRELU, training, bump)
+        z, part = _conv_bn(ops.conv_down, ops.conv_down_stats, y, wd, training)
+        y, stats = _bn_act(z, bn, ACT_LRELU, training, part, bump)
         ctx.enc.append(_BnSave(z if save else None, y, stats))
     # 4x4 valid conv to the 100-d bottleneck (model.py:107-109)
     wd, _ = pk.get(head_conv.weight, True, False)
@@ -381,7 +374,8 @@ def generator_forward(mod, x, save=True):
     ctx.dec = []
     for conv, bn in zip(dec_convs[1:-1], dec_bns[1:]):
         _, wu = pk.get(conv.weight, True, True)
-        z, y, stats = _conv_bn_act("up", y, wu, bn, ACT_RELU, training, bump)
+        z, part = _conv_bn(ops.conv_up, ops.conv_up_stats, y, wu, training)
+        y, stats = _bn_act(z, bn, ACT_RELU, training, part, bump)
         ctx.dec.append(_BnSave(z if save else None, y, stats))
     _, wu3 = pk.get_c3(dec_convs[-1].weight)
     out = ops.c3_up_tc(y, wu3, sigmoid=True)

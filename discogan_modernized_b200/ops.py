@@ -152,50 +152,6 @@ def conv_up_stats(small, wu):
     return out, part
 
 
-_stat_acc = {}
-
-
-def _bn_fuse_buffers(device):
-    """Zeroed fp32[8192] accumulator + int32 counter for the in-kernel BatchNorm finalize (left zeroed by the kernel)."""
-    acc = _stat_acc.get(device)
-    if acc is None:
-        if torch.cuda.is_current_stream_capturing():
-            raise KernelError("BN accumulator would be allocated during CUDA-graph capture; run one eager step first")
-        acc = torch.zeros(8192, dtype=F32, device=device)
-        _stat_acc[device] = acc
-    return acc, counters(device)[300:301]
-
-
-def _conv_bn(mode, x, w, gamma, beta, running_mean, running_var, eps, momentum):
-    if mode == 0:
-        B, H, W, Cb = x.shape
-        Cs, Hs, Ws, N = w.shape[0], H // 2, W // 2, w.shape[0]
-        out = torch.empty(B, Hs, Ws, Cs, dtype=BF16, device=x.device)
-    else:
-        B, Hs, Ws, Cs = x.shape
-        Cb, N = w.shape[0], w.shape[0]
-        out = torch.empty(B, 2 * Hs, 2 * Ws, Cb, dtype=BF16, device=x.device)
-    if N > 4096:
-        raise KernelError(f"fused BatchNorm statistics support at most 4096 channels, got {N}")
-    stats = torch.empty(4, N, dtype=F32, device=x.device)
-    acc, counter = _bn_fuse_buffers(x.device)
-    check(lib().dg_conv4x4s2_fprop_bn(mode, _ptr(x, BF16, "x"), _ptr(w, BF16, "w"), _ptr(out), B, Hs, Ws, Cs, Cb,
-                                      _ptr(gamma, F32, "gamma"), _ptr(beta, F32, "beta"), eps, momentum, _ptr(stats),
-                                      _ptr(running_mean, F32, "running_mean"), _ptr(running_var, F32, "running_var"),
-                                      acc.data_ptr(), counter.data_ptr(), _stream()), "dg_conv4x4s2_fprop_bn")
-    return out, stats
-
-
-def conv_down_bn(big, wd, gamma, beta, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
-    """Conv2d 4x4 s2 p1 forward + training-mode BatchNorm statistics of its output in one launch -> (z, stats[4,Cs])."""
-    return _conv_bn(0, big, wd, gamma, beta, running_mean, running_var, eps, momentum)
-
-
-def conv_up_bn(small, wu, gamma, beta, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
-    """ConvTranspose2d 4x4 s2 p1 forward + BatchNorm statistics in one launch -> (z, stats[4,Cb])."""
-    return _conv_bn(1, small, wu, gamma, beta, running_mean, running_var, eps, momentum)
-
-
 def conv_wgrad(small, big, dw, beta=1.0):
     """dw[Cs,Cb,4,4] = beta*dw + sum_pixels small (x) shifted big."""
     B, Hs, Ws, Cs = small.shape
@@ -330,21 +286,6 @@ def fc_wgrad(small2d, big2d, dw, beta=1.0):
 
 
 # ---- BatchNorm + activation -----------------------------------------------------------------
-_counters = {}
-
-
-def counters(device):
-    """Zero-initialised int32[512] used by kernels that finish a reduction in their last-arriving block; every
-    kernel leaves it zeroed again."""
-    buf = _counters.get(device)
-    if buf is None:
-        if torch.cuda.is_current_stream_capturing():
-            raise KernelError("counter buffer would be allocated during CUDA-graph capture; run one eager step first")
-        buf = torch.zeros(512, dtype=torch.int32, device=device)
-        _counters[device] = buf
-    return buf
-
-
 def _bn_scratch(P, C, device):
     n = lib().dg_bn_scratch_floats(P, C)
     return scratch("bn", 4 * n, device)
@@ -401,7 +342,7 @@ def bn_act_bwd(dy2d, y2d, z2d, stats, gamma, act, slope=0.2, dgamma=None, dbeta=
     check(lib().dg_bn_act_bwd(_ptr(dy2d, BF16, "dy"), _ptr(dy2, BF16, "dy2"), _ptr(bcast, F32, "bcast"), bcast_coef, bcast_rows,
                               _ptr(y2d, BF16, "y"), _ptr(z2d, BF16, "z"), _ptr(stats, F32, "stats"), _ptr(gamma, F32, "gamma"),
                               P, C, act, slope, _ptr(dgamma, F32, "dgamma"), _ptr(dbeta, F32, "dbeta"), grad_beta, _ptr(dz),
-                              _ptr(coefs), sc.data_ptr(), counters(z2d.device).data_ptr(), _stream()), "dg_bn_act_bwd")
+                              _ptr(coefs), sc.data_ptr(), _stream()), "dg_bn_act_bwd")
     return dz
 
 

@@ -58,12 +58,6 @@ int dg_conv4x4s2_fprop_stats(const void* x_big, const void* wd, void* z_small, f
                              int Cb, int Cs, dg_stream_t stream);
 int dg_convT4x4s2_fprop_stats(const void* x_small, const void* wu, void* y_big, float* stat_part, int B, int Hs, int Ws,
                               int Cs, int Cb, dg_stream_t stream);
-/* forward convolution + the complete training-mode BatchNorm statistics of its output in one launch (last-CTA
- * finalize): mode 0 Conv2d fprop (x big -> z small), mode 1 ConvTranspose2d fprop (x small -> z big).  acc = float[2*N]
- * and counter = int, both zeroed once by the caller and left zeroed; stats = float[4*N]; running_* may be NULL. */
-int dg_conv4x4s2_fprop_bn(int mode, const void* x, const void* w_packed, void* z, int B, int Hs, int Ws, int Cs, int Cb,
-                          const float* gamma, const float* beta, float eps, float momentum, float* stats,
-                          float* running_mean, float* running_var, float* acc, int* counter, dg_stream_t stream);
 /* same, fused with the LeakyReLU derivative of the (BN-less) layer that produced x: dx *= (mask>0 ? 1 : slope) */
 int dg_conv4x4s2_dgrad_masked(const void* dz_small, const void* wu, void* dx_big, const void* mask, float slope, int B,
                               int Hs, int Ws, int Cs, int Cb, dg_stream_t stream);
@@ -125,7 +119,7 @@ int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats
 int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bcast_coef, long long bcast_rows,
                   const void* y, const void* z, const float* stats, const float* gamma, long long P, int C, int act,
                   float slope, float* dgamma, float* dbeta, float grad_beta, void* dz, float* coefs, float* scratch,
-                  int* counters /* int[256], zero-initialised once; self-resetting */, dg_stream_t stream);
+                  dg_stream_t stream);
 
 /* ---- losses ----
  * nn.Sigmoid (model.py:36) + nn.BCELoss in get_gan_loss, image_translation.py:146-168,268 */
