@@ -18,6 +18,7 @@
 //
 // Kernel shape: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM owner), warps 2-5 = epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tma_host.cuh"
@@ -169,6 +170,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+      // descriptors differ only in the 14-bit start-address field: build the constant part once and add the
+      // (stage, k) offset per MMA so the single issuing thread spends a handful of instructions per tcgen05.mma
+      const uint64_t desc_base = make_sdesc_sw128(0, 16, 1024);
+      const uint32_t smem0 = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -180,14 +185,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int it = 0; it < p.k_iters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + kATileBytes;
+          const uint32_t sa = smem0 + (uint32_t)(stage * stage_bytes);
+          const uint64_t da0 = desc_base | (uint64_t)((sa & 0x3FFFFu) >> 4);
+          const uint64_t db0 = desc_base | (uint64_t)(((sa + kATileBytes) & 0x3FFFFu) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = make_sdesc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = make_sdesc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(d_tmem, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == p.num_stages) {
             stage = 0;
@@ -347,11 +350,14 @@ struct WgradParams {
   float* dw;  // direct mode (splits == 1): the epilogue writes dw = beta*dw + acc in PyTorch layout itself
   float beta;
   int direct;
+  int share;  // 0: one TMA box per tap.  1/2: taps that differ by a one-pixel shift inside the same parity plane share a
+              // 33-pixel box and are addressed with a 128-byte row offset (1: descriptor base_offset = row phase, 2: 0)
 };
+constexpr int kWgSlot = 5 * 1024;  // 33 pixels x 128 B, padded to the 1024-byte swizzle repeat
 
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmBig,
-                  const WgradParams p) {
+                  const __grid_constant__ CUtensorMap tmBig33, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -403,9 +409,19 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = smem + stage * kWgStageBytes;
         uint8_t* sb = sa + 2 * kWgBoxBytes;
-        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)kWgStageBytes);
+        mbar_arrive_expect_tx(&full_bar[stage],
+                              p.share ? (uint32_t)(2 * kWgBoxBytes + 4 * 33 * 128) : (uint32_t)kWgStageBytes);
         tma_load_4d(sa, &tmS, &full_bar[stage], mt * 128, w0, h0, b0);
         tma_load_4d(sa + kWgBoxBytes, &tmS, &full_bar[stage], mt * 128 + 64, w0, h0, b0);
+        if (p.share) {
+#pragma unroll
+          for (int s4 = 0; s4 < 4; ++s4) {
+            const int kh = half * 2 + (s4 >> 1), pw = s4 & 1;
+            const int dh = ((kh + 1) >> 1) - 1, ph = (kh + 1) & 1;
+            tma_load_5d(sb + s4 * kWgSlot, &tmBig33, &full_bar[stage], pw * p.Cb + nt * 64, w0 + (pw ? -1 : 0), ph,
+                        h0 + dh, b0);
+          }
+        } else
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           const int tap = half * 8 + t;
@@ -422,7 +438,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      // One tcgen05.mma covers FOUR taps: their 64-channel boxes sit 4 KB apart in shared memory, which is exactly an
+      // MN-major B operand with N = 256 and LBO = 4 KB, so a K-step needs 2 instructions instead of 8 (the single
+      // issuing thread was the bottleneck at N = 64: 32 tensor-clocks of work per instruction).
+      const uint32_t idesc = make_idesc_bf16(128, p.share ? 64 : 256, 1, 1);
+      const uint64_t desc_base = make_sdesc_sw128(0, kWgBoxBytes, 1024);
       int stage = 0;
       uint32_t phase = 0;
       for (int ch = chunk_begin; ch < chunk_end; ++ch) {
@@ -432,12 +452,25 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
         const uint32_t sb = sa + 2 * kWgBoxBytes;
 #pragma unroll
         for (int ks = 0; ks < kWgKC / 16; ++ks) {
+          const uint32_t accum = (ch > chunk_begin || ks > 0) ? 1u : 0u;
           // MN-major SW128: LBO = distance between 64-wide MN blocks, SBO = distance between 8-row K groups
-          const uint64_t da = make_sdesc_sw128(sa + ks * 2048, kWgBoxBytes, 1024);
+          const uint64_t da = desc_base | (uint64_t)(((sa + ks * 2048) & 0x3FFFFu) >> 4);
+          if (p.share) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const uint64_t db = make_sdesc_sw128(sb + t * kWgBoxBytes + ks * 2048, kWgBoxBytes, 1024);
-            umma_bf16(tmem_base + (uint32_t)(t * 64), da, db, idesc, (ch > chunk_begin || ks > 0) ? 1u : 0u);
+            for (int t = 0; t < 8; ++t) {
+              const int kw = t & 3, pw = (kw + 1) & 1, dw = ((kw + 1) >> 1) - 1;
+              const uint32_t rowoff = (uint32_t)(dw - (pw ? -1 : 0));
+              const uint32_t addr = sb + (uint32_t)(((t >> 2) * 2 + pw) * kWgSlot) + rowoff * 128u + ks * 2048u;
+              // a start address that is not 1024-byte aligned works with base_offset 0: the swizzle XOR is taken from
+              // the absolute shared-memory address bits (verified on B200, DG_WGRAD_SHARE=2)
+              umma_bf16(tmem_base + (uint32_t)(t * 64), da, desc_base | (uint64_t)((addr & 0x3FFFFu) >> 4), idesc, accum);
+            }
+          } else {
+#pragma unroll
+            for (int tq = 0; tq < 2; ++tq) {
+              const uint32_t addr = sb + (uint32_t)(tq * 4 * kWgBoxBytes) + ks * 2048u;
+              umma_bf16(tmem_base + (uint32_t)(tq * 256), da, desc_base | (uint64_t)((addr & 0x3FFFFu) >> 4), idesc, accum);
+            }
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -739,10 +772,18 @@ int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta
                    ((uintptr_t)ws & 15) == 0,
                "wgrad: pointers must be 16-byte aligned");
   p.ws = reinterpret_cast<float*>(ws);
-  CUtensorMap tmS, tmBig;
+  static int share_mode = -1;
+  if (share_mode < 0) {
+    const char* e = getenv("DG_WGRAD_SHARE");
+    share_mode = e ? atoi(e) : 0;
+  }
+  p.share = (share_mode > 0 && p.Wt == 32 && p.Ht == 1 && p.Bt == 1) ? 2 : 0;
+  CUtensorMap tmS, tmBig, tmBig33;
   int rc = make_nhwc_map(&tmS, small, B, Hs, Ws, Cs, p.Wt, p.Ht, p.Bt);
   if (rc) return rc;
   rc = make_parity_map(&tmBig, big, B, 2 * Hs, 2 * Ws, Cb, p.Wt, p.Ht, p.Bt);
+  if (rc) return rc;
+  rc = make_parity_map(&tmBig33, big, B, 2 * Hs, 2 * Ws, Cb, p.share ? 33 : p.Wt, p.Ht, p.Bt);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
@@ -755,7 +796,7 @@ int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta
   }
   const int smem_bytes = kWgStages * kWgStageBytes + 1024 + 256;
   dim3 grid(p.m_tiles * p.n_tiles * 2, p.splits);
-  wgrad_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmS, tmBig, p);
+  wgrad_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmS, tmBig, tmBig33, p);
   DG_CHECK_LAUNCH("wgrad_gemm_kernel");
   if (p.direct) return DG_OK;
   const long long total = (long long)Cs * Cb * 2;

@@ -265,12 +265,25 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ part_sum, con
   __shared__ double sh_s[8][32], sh_q[8][32];
   const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
-  double s = 0.0, q = 0.0;
-  if (c < C)
-    for (int i = sy; i < splits; i += 8) {
-      s += (double)part_sum[(size_t)i * C + c];
-      q += (double)part_sq[(size_t)i * C + c];
+  // fp32 running sums per lane (4 independent chains), double only for the final combine: FP64 add chains are an
+  // order of magnitude slower on this part
+  float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    int i = sy;
+    for (; i + 24 < splits; i += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        fs[u] += part_sum[(size_t)(i + 8 * u) * C + c];
+        fq[u] += part_sq[(size_t)(i + 8 * u) * C + c];
+      }
     }
+    for (; i < splits; i += 8) {
+      fs[0] += part_sum[(size_t)i * C + c];
+      fq[0] += part_sq[(size_t)i * C + c];
+    }
+  }
+  double s = ((double)fs[0] + (double)fs[1]) + ((double)fs[2] + (double)fs[3]);
+  double q = ((double)fq[0] + (double)fq[1]) + ((double)fq[2] + (double)fq[3]);
   sh_s[sy][cx] = s;
   sh_q[sy][cx] = q;
   __syncthreads();
@@ -431,12 +444,23 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part_g, const f
   __shared__ double sh_s[8][32], sh_q[8][32];
   const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
-  double sg = 0.0, sgx = 0.0;
-  if (c < C)
-    for (int i = sy; i < splits; i += 8) {
-      sg += (double)part_g[(size_t)i * C + c];
-      sgx += (double)part_gx[(size_t)i * C + c];
+  float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    int i = sy;
+    for (; i + 24 < splits; i += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        fs[u] += part_g[(size_t)(i + 8 * u) * C + c];
+        fq[u] += part_gx[(size_t)(i + 8 * u) * C + c];
+      }
     }
+    for (; i < splits; i += 8) {
+      fs[0] += part_g[(size_t)i * C + c];
+      fq[0] += part_gx[(size_t)i * C + c];
+    }
+  }
+  double sg = ((double)fs[0] + (double)fs[1]) + ((double)fs[2] + (double)fs[3]);
+  double sgx = ((double)fq[0] + (double)fq[1]) + ((double)fq[2] + (double)fq[3]);
   sh_s[sy][cx] = sg;
   sh_q[sy][cx] = sgx;
   __syncthreads();
