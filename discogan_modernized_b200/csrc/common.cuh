@@ -205,6 +205,11 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// fire-and-forget 16-byte float accumulation in L2 (REDG.E.ADD.F32x4): no load round trip in the issuing thread
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- descriptors (bit layouts follow CUTLASS cute/arch/mma_sm100_desc.hpp) ----
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32.
 //   [4,6) c_format=1 (F32)  [7,10) a_format=1 (BF16)  [10,13) b_format=1 (BF16)

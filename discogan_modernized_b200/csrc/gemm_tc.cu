@@ -502,6 +502,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
                                   __uint_as_float(r[3][j]));
           float4 o1 = make_float4(__uint_as_float(r[4][j]), __uint_as_float(r[5][j]), __uint_as_float(r[6][j]),
                                   __uint_as_float(r[7][j]));
+          if (p.beta == 1.f) {   // accumulate: vector reductions in L2 keep the epilogue free of load round trips
+            red_add_f32x4(d, o0.x, o0.y, o0.z, o0.w);
+            red_add_f32x4(d + 4, o1.x, o1.y, o1.z, o1.w);
+            continue;
+          }
           if (p.beta != 0.f) {
             const float4 a0 = *reinterpret_cast<const float4*>(d);
             const float4 a1 = *reinterpret_cast<const float4*>(d + 4);
