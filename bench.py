@@ -253,8 +253,9 @@ def measure_roofline(tr, batches, torch, pk):
 
     for n, f in orig.items():
         setattr(ops, n, wrap(n, f, names[n]))
-    saved_graphs = tr.use_graphs
-    tr.use_graphs = False                      # per-launch events need eager launches
+    saved_graphs, saved_side = tr.use_graphs, tr._side
+    tr.use_graphs = False                      # per-launch events need eager launches ...
+    tr._side = None                            # ... on one stream (no concurrent lane sharing the SMs)
     try:
         for cycle in range(2):                 # first cycle: untimed, lets the caching allocator grow its eager pool
             recs.clear()                       # (cudaMalloc stalls between the events would be charged to kernels)
@@ -263,7 +264,7 @@ def measure_roofline(tr, batches, torch, pk):
                 tr.step(A, B)
             torch.cuda.synchronize()
     finally:
-        tr.use_graphs = saved_graphs
+        tr.use_graphs, tr._side = saved_graphs, saved_side
         for n, f in orig.items():
             setattr(ops, n, f)
     by, layers = {}, {}
@@ -342,7 +343,7 @@ def run_b200(args, S, B):
         "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(S, B), "image_size": S, "batch_per_gpu": B, "global_batch": B * world,
-                   "model_arch": args.model_arch, "parallelism": f"dp{world}", "cuda_graphs": bool(tr.use_graphs),
+                   "model_arch": args.model_arch, "parallelism": f"dp{world}", "cuda_graphs": bool(tr.use_graphs), "lanes": 2 if tr._side is not None else 1,
                    "l2": "per-step working set (weights+grads+Adam moments+activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "image-pairs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / steps},

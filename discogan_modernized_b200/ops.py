@@ -33,10 +33,18 @@ scratch_generation = 0   # bumped whenever a scratch buffer is (re)allocated: ca
                          # pointer must be re-captured (train_step.DiscoGANTrainer checks this before every replay)
 
 
+_lane = 0   # the trainer runs independent sub-chains of the step on two streams ("lanes"); each lane has its own scratch
+
+
+def set_lane(i):
+    global _lane
+    _lane = i
+
+
 def scratch(kind, nbytes, device):
-    """Grow-only per-device scratch buffers (wgrad workspace, BN partials, reduction partials)."""
+    """Grow-only per-device, per-lane scratch buffers (wgrad workspace, BN partials, reduction partials)."""
     global scratch_generation
-    key = (kind, device)
+    key = (kind, device, _lane)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():

@@ -20,6 +20,7 @@ as one hand-scheduled forward/backward over the kernel engines in ``model.py``:
   per (step kind, loss weights) into a CUDA graph and replayed: inputs are copied into static
   buffers, the Adam step counter lives on the device.
 """
+import contextlib
 import os
 
 import torch
@@ -194,6 +195,8 @@ class DiscoGANTrainer:
         self._static = {}        # batch -> (A, B) static input buffers
         self._pool = None
         self._scratch_gen = -1
+        use_lanes = os.environ.get("DISCOGAN_B200_LANES", "1") != "0"
+        self._side = torch.cuda.Stream(device=self.device) if use_lanes else None
         self._graph_launches = {}   # kernels inside each captured graph
         self.kernel_launches = 0    # kernels of this library launched (eagerly or by graph replay) by step()
 
@@ -260,31 +263,69 @@ class DiscoGANTrainer:
         self.iters += 1
         return is_dis
 
+    # ------------------------------------------------------------------------------------------
+    # two "lanes" (streams): the A->B->A and B->A->B halves of the step are independent between a few join points,
+    # and at 64x64 most kernels are far too small to fill 148 SMs, so running the halves concurrently hides their
+    # latency.  Inside a phase the two lanes never touch the same network, gradient buffer or scratch buffer.
+    def _fork(self):
+        if self._side is not None:
+            self._side.wait_stream(torch.cuda.current_stream())
+
+    def _join(self):
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+
+    @contextlib.contextmanager
+    def _lane(self, i):
+        if i == 0 or self._side is None:
+            yield
+            return
+        ops.set_lane(1)
+        try:
+            with torch.cuda.stream(self._side):
+                yield
+        finally:
+            ops.set_lane(0)
+
     def _step_impl(self, A, B, is_dis, rate):
         co = loss_coefficients(self.model_arch, rate)
         G_A, G_B, D_A, D_B = self.G_A, self.G_B, self.D_A, self.D_B
         save_g = not is_dis
-        AB, c_gb1 = generator_forward(G_B, A, save=save_g)       # A -> B
-        BA, c_ga1 = generator_forward(G_A, B, save=save_g)       # B -> A
-        ABA, c_ga2 = generator_forward(G_A, AB, save=save_g)     # A -> B -> A
-        BAB, c_gb2 = generator_forward(G_B, BA, save=save_g)     # B -> A -> B
-        ops.mse_fwd(ABA, A, self.loss_buf[6:7])
-        ops.mse_fwd(BAB, B, self.loss_buf[7:8])
-        da = self._disc_pair(D_A, A, BA, 0, save_real=is_dis, save_fake=True)
-        db = self._disc_pair(D_B, B, AB, 1, save_real=is_dis, save_fake=True)
+        lane, fork, join = self._lane, self._fork, self._join
+        fork()
+        with lane(0):
+            AB, c_gb1 = generator_forward(G_B, A, save=save_g)       # A -> B
+        with lane(1):
+            BA, c_ga1 = generator_forward(G_A, B, save=save_g)       # B -> A
+        join(); fork()                                               # each net's second pass follows its first
+        with lane(0):
+            ABA, c_ga2 = generator_forward(G_A, AB, save=save_g)     # A -> B -> A
+            ops.mse_fwd(ABA, A, self.loss_buf[6:7])
+        with lane(1):
+            BAB, c_gb2 = generator_forward(G_B, BA, save=save_g)     # B -> A -> B
+            ops.mse_fwd(BAB, B, self.loss_buf[7:8])
+        with lane(0):
+            da = self._disc_pair(D_A, A, BA, 0, save_real=is_dis, save_fake=True)
+        with lane(1):
+            db = self._disc_pair(D_B, B, AB, 1, save_real=is_dis, save_fake=True)
+        join()
 
         red = self.reducer
         if is_dis:
             stepped = []
-            for D, d, c in ((D_A, da, co["dis_A"]), (D_B, db, co["dis_B"])):
+            fork()
+            for i, (D, d, c) in enumerate(((D_A, da, co["dis_A"]), (D_B, db, co["dis_B"]))):
                 if c == 0.0:
                     continue
                 self.flat[D].zero_grad()
-                dlr, dlf = ops.gan_bce_bwd(d["p_real"], d["p_fake"], c, 0.0)
-                discriminator_backward(D, d["ctx_r"], dlr, need_dx=False, need_wgrad=True)
-                discriminator_backward(D, d["ctx_f"], dlf, need_dx=False, need_wgrad=True)
-                red.launch(self.flat[D].flat_g)
+                with lane(i):
+                    dlr, dlf = ops.gan_bce_bwd(d["p_real"], d["p_fake"], c, 0.0)
+                    discriminator_backward(D, d["ctx_r"], dlr, need_dx=False, need_wgrad=True)
+                    discriminator_backward(D, d["ctx_f"], dlf, need_dx=False, need_wgrad=True)
                 stepped.append(D)
+            join()
+            for D in stepped:
+                red.launch(self.flat[D].flat_g)
         else:
             use_a = co["gen_A"] != 0.0 or co["fm_A"] != 0.0      # losses through D_A(BA): reach G_A pass 1
             use_b = co["gen_B"] != 0.0 or co["fm_B"] != 0.0      # losses through D_B(AB): reach G_B pass 1
@@ -295,33 +336,41 @@ class DiscoGANTrainer:
                 stepped.append(G_A)
             for G in stepped:
                 self.flat[G].zero_grad()
-            # ---- everything that ends in G_B's first pass (input A): D_B(AB) and G_A(AB) -> ABA
-            dAB = None
-            if use_b:
-                dAB = self._disc_fake_backward(D_B, db, co["gen_B"], co["fm_B"], AB.shape[0])
-            if co["recon_A"] != 0.0:
-                dABA = ops.mse_bwd(ABA, A, co["recon_A"])
-                dAB = generator_backward(G_A, c_ga2, dABA, need_dx=True, need_wgrad=True, dx_out=dAB,
-                                         dx_accumulate=dAB is not None)
-            if dAB is not None:
-                generator_backward(G_B, c_gb1, dAB, need_dx=False, need_wgrad=True)
-            # ---- everything that ends in G_A's first pass (input B): D_A(BA) and G_B(BA) -> BAB
-            dBA = None
-            if use_a:
-                dBA = self._disc_fake_backward(D_A, da, co["gen_A"], co["fm_A"], BA.shape[0])
-            if co["recon_B"] != 0.0:
-                dBAB = ops.mse_bwd(BAB, B, co["recon_B"])
-                dBA = generator_backward(G_B, c_gb2, dBAB, need_dx=True, need_wgrad=True, dx_out=dBA,
-                                         dx_accumulate=dBA is not None)
-            if G_B in stepped:
-                red.launch(self.flat[G_B].flat_g)                # G_B is complete: overlap with G_A's last pass
-            if dBA is not None:
-                generator_backward(G_A, c_ga1, dBA, need_dx=False, need_wgrad=True)
-            if G_A in stepped:
-                red.launch(self.flat[G_A].flat_g)
+            dAB = dBA = None
+            fork()
+            # phase A: the discriminators' fake passes, data gradients only  (lane 0: D_B(AB), lane 1: D_A(BA))
+            # phase B: the generators' second passes                          (lane 0: G_A(AB)->ABA, lane 1: G_B(BA)->BAB)
+            with lane(0):
+                if use_b:
+                    dAB = self._disc_fake_backward(D_B, db, co["gen_B"], co["fm_B"], AB.shape[0])
+                if co["recon_A"] != 0.0:
+                    dABA = ops.mse_bwd(ABA, A, co["recon_A"])
+                    dAB = generator_backward(G_A, c_ga2, dABA, need_dx=True, need_wgrad=True, dx_out=dAB,
+                                             dx_accumulate=dAB is not None)
+            with lane(1):
+                if use_a:
+                    dBA = self._disc_fake_backward(D_A, da, co["gen_A"], co["fm_A"], BA.shape[0])
+                if co["recon_B"] != 0.0:
+                    dBAB = ops.mse_bwd(BAB, B, co["recon_B"])
+                    dBA = generator_backward(G_B, c_gb2, dBAB, need_dx=True, need_wgrad=True, dx_out=dBA,
+                                             dx_accumulate=dBA is not None)
+            join(); fork()
+            # phase C: the generators' first passes (each accumulates into the gradients its second pass just wrote)
+            with lane(0):
+                if dAB is not None:
+                    generator_backward(G_B, c_gb1, dAB, need_dx=False, need_wgrad=True)
+            with lane(1):
+                if dBA is not None:
+                    generator_backward(G_A, c_ga1, dBA, need_dx=False, need_wgrad=True)
+            join()
+            for G in stepped:
+                red.launch(self.flat[G].flat_g)
         red.join()
-        for n in stepped:
-            self.flat[n].adam(self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, red.grad_scale)
+        fork()
+        for i, n in enumerate(stepped):
+            with lane(i):
+                self.flat[n].adam(self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, red.grad_scale)
+        join()
 
     def _disc_fake_backward(self, D, d, c_gen, c_fm, B):
         """Back-prop c_gen*gen_loss + c_fm*fm_loss through the fake pass of D down to its input image."""
