@@ -253,7 +253,7 @@ def measure_roofline(tr, batches, torch, pk):
 
     for n, f in orig.items():
         setattr(ops, n, wrap(n, f, names[n]))
-    saved_graphs, saved_side = tr.use_graphs, tr._side
+    saved_graphs, saved_side = tr.use_graphs, tr._side  # (_streams() is empty when _side is None)
     tr.use_graphs = False                      # per-launch events need eager launches ...
     tr._side = None                            # ... on one stream (no concurrent lane sharing the SMs)
     try:

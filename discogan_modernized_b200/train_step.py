@@ -196,15 +196,17 @@ class DiscoGANTrainer:
         self._pool = None
         self._scratch_gen = -1
         use_lanes = os.environ.get("DISCOGAN_B200_LANES", "1") != "0"
-        self._side = torch.cuda.Stream(device=self.device) if use_lanes else None
+        self._side = torch.cuda.Stream(device=self.device) if use_lanes else None          # lane 1
+        self._more = [torch.cuda.Stream(device=self.device) for _ in range(2)] if use_lanes else []   # lanes 2, 3
         self._graph_launches = {}   # kernels inside each captured graph
         self.kernel_launches = 0    # kernels of this library launched (eagerly or by graph replay) by step()
 
     # ------------------------------------------------------------------------------------------
-    def _disc_pair(self, D, real_img, fake_img, slot, save_real, save_fake):
-        """Both passes of one discriminator + its BCE and FM losses (image_translation.py:353-364)."""
-        lr_, feats_r, ctx_r = discriminator_forward(D, real_img, save=save_real)
-        lf_, feats_f, ctx_f = discriminator_forward(D, fake_img, save=save_fake)
+    def _disc_fake_and_losses(self, D, real, fake_img, slot):
+        """The fake pass of one discriminator + its BCE and FM losses against the real pass
+        (image_translation.py:353-364)."""
+        lr_, feats_r, ctx_r = real
+        lf_, feats_f, ctx_f = discriminator_forward(D, fake_img, save=True)
         buf = self.loss_buf
         p_real, p_fake = ops.gan_bce_fwd(lr_, lf_, buf[2 * slot:2 * slot + 2])
         fm_out = buf[4 + slot:5 + slot]
@@ -267,22 +269,25 @@ class DiscoGANTrainer:
     # two "lanes" (streams): the A->B->A and B->A->B halves of the step are independent between a few join points,
     # and at 64x64 most kernels are far too small to fill 148 SMs, so running the halves concurrently hides their
     # latency.  Inside a phase the two lanes never touch the same network, gradient buffer or scratch buffer.
-    def _fork(self):
-        if self._side is not None:
-            self._side.wait_stream(torch.cuda.current_stream())
+    def _streams(self):
+        return ([self._side] + self._more) if self._side is not None else []
 
-    def _join(self):
-        if self._side is not None:
-            torch.cuda.current_stream().wait_stream(self._side)
+    def _fork(self, n=2):
+        for st in self._streams()[:n - 1]:
+            st.wait_stream(torch.cuda.current_stream())
+
+    def _join(self, n=2):
+        for st in self._streams()[:n - 1]:
+            torch.cuda.current_stream().wait_stream(st)
 
     @contextlib.contextmanager
     def _lane(self, i):
         if i == 0 or self._side is None:
             yield
             return
-        ops.set_lane(1)
+        ops.set_lane(i)
         try:
-            with torch.cuda.stream(self._side):
+            with torch.cuda.stream(self._streams()[i - 1]):
                 yield
         finally:
             ops.set_lane(0)
@@ -292,23 +297,30 @@ class DiscoGANTrainer:
         G_A, G_B, D_A, D_B = self.G_A, self.G_B, self.D_A, self.D_B
         save_g = not is_dis
         lane, fork, join = self._lane, self._fork, self._join
-        fork()
+        # forward, phase 1 (4 lanes): the two first generator passes and the two real discriminator passes
+        fork(4)
         with lane(0):
             AB, c_gb1 = generator_forward(G_B, A, save=save_g)       # A -> B
         with lane(1):
             BA, c_ga1 = generator_forward(G_A, B, save=save_g)       # B -> A
-        join(); fork()                                               # each net's second pass follows its first
+        with lane(2):
+            real_a = discriminator_forward(D_A, A, save=is_dis)
+        with lane(3):
+            real_b = discriminator_forward(D_B, B, save=is_dis)
+        join(4); fork(4)
+        # phase 2: second generator passes + reconstruction losses, fake discriminator passes + GAN / FM losses
+        # (every network's second pass follows its first: BatchNorm running statistics advance in reference order)
         with lane(0):
             ABA, c_ga2 = generator_forward(G_A, AB, save=save_g)     # A -> B -> A
             ops.mse_fwd(ABA, A, self.loss_buf[6:7])
         with lane(1):
             BAB, c_gb2 = generator_forward(G_B, BA, save=save_g)     # B -> A -> B
             ops.mse_fwd(BAB, B, self.loss_buf[7:8])
-        with lane(0):
-            da = self._disc_pair(D_A, A, BA, 0, save_real=is_dis, save_fake=True)
-        with lane(1):
-            db = self._disc_pair(D_B, B, AB, 1, save_real=is_dis, save_fake=True)
-        join()
+        with lane(2):
+            da = self._disc_fake_and_losses(D_A, real_a, BA, 0)
+        with lane(3):
+            db = self._disc_fake_and_losses(D_B, real_b, AB, 1)
+        join(4)
 
         red = self.reducer
         if is_dis:
