@@ -298,14 +298,16 @@ class DiscoGANTrainer:
         save_g = not is_dis
         lane, fork, join = self._lane, self._fork, self._join
         # forward, phase 1 (4 lanes): the two first generator passes and the two real discriminator passes
+        # (big images fill the GPU with single kernels: the discriminators then share lanes 0/1 with the generators)
+        l2, l3 = (2, 3) if self.image_size <= 128 else (0, 1)
         fork(4)
         with lane(0):
             AB, c_gb1 = generator_forward(G_B, A, save=save_g)       # A -> B
         with lane(1):
             BA, c_ga1 = generator_forward(G_A, B, save=save_g)       # B -> A
-        with lane(2):
+        with lane(l2):
             real_a = discriminator_forward(D_A, A, save=is_dis)
-        with lane(3):
+        with lane(l3):
             real_b = discriminator_forward(D_B, B, save=is_dis)
         join(4); fork(4)
         # phase 2: second generator passes + reconstruction losses, fake discriminator passes + GAN / FM losses
@@ -316,9 +318,9 @@ class DiscoGANTrainer:
         with lane(1):
             BAB, c_gb2 = generator_forward(G_B, BA, save=save_g)     # B -> A -> B
             ops.mse_fwd(BAB, B, self.loss_buf[7:8])
-        with lane(2):
+        with lane(l2):
             da = self._disc_fake_and_losses(D_A, real_a, BA, 0)
-        with lane(3):
+        with lane(l3):
             db = self._disc_fake_and_losses(D_B, real_b, AB, 1)
         join(4)
 
