@@ -185,7 +185,9 @@ def _bn_act_bwd(dy, sv, bn, act, need_wgrad, dy2=None, bcast=None, bcast_coef=0.
 def _conv1_backward(pk, weight, ctx, dz1, need_dx, need_wgrad, dx_out, dx_accumulate):
     """Backward of the image-side Conv2d(3,64,4,2,1)+LeakyReLU given dz1 = d(loss)/d(pre-activation)."""
     if need_wgrad:
-        ops.c3_wgrad_tc(dz1, ctx.xp, *_grad_buf(weight))
+        ctx.keep.append(dz1)
+        with ops.wgrad_side():
+            ops.c3_wgrad_tc(dz1, ctx.xp, *_grad_buf(weight))
     if not need_dx:
         return None
     _, wu3 = pk.get_c3(weight)
@@ -196,7 +198,7 @@ def _conv1_backward(pk, weight, ctx, dz1, need_dx, need_wgrad, dx_out, dx_accumu
 # Discriminator
 # ---------------------------------------------------------------------------------------------
 class _DiscCtx:
-    __slots__ = ("xp", "y1", "bn", "B", "shape")
+    __slots__ = ("xp", "y1", "bn", "B", "shape", "keep")
 
 
 def discriminator_forward(mod, x, save=True):
@@ -210,6 +212,7 @@ def discriminator_forward(mod, x, save=True):
     wc, _ = pk.get_c3(mod.conv1.weight)
     y = ops.c3_down_tc(xp, wc, ACT_LRELU, LRELU_SLOPE)
     ctx = _DiscCtx()
+    ctx.keep = []   # tensors used by kernels on the wgrad side stream: kept alive until the context is dropped
     ctx.xp, ctx.y1, ctx.bn, ctx.B, ctx.shape = (xp if save else None), y, [], x.shape[0], x.shape
     feats = []
     for k in range(2, mod.n_down + 1):
@@ -236,7 +239,9 @@ def discriminator_backward(mod, ctx, dlogit, dfeats=None, fm_bcast=None, need_dx
     y_last = ctx.bn[-1].y
     dl = dlogit.contiguous().view(B, 1)
     if need_wgrad:
-        ops.fc_wgrad(dl, y_last.view(B, -1), *_grad_buf(head.weight))
+        ctx.keep.append(dl)
+        with ops.wgrad_side():
+            ops.fc_wgrad(dl, y_last.view(B, -1), *_grad_buf(head.weight))
     dy = ops.fc_up(dl, wd.view(1, -1)).view(y_last.shape)
     for k in range(mod.n_down, 1, -1):
         i = k - 2
@@ -247,7 +252,9 @@ def discriminator_backward(mod, ctx, dlogit, dfeats=None, fm_bcast=None, need_dx
         dz = _bn_act_bwd(dy, sv, bn, ACT_LRELU, need_wgrad, dy2, bc, coef)
         y_prev = ctx.bn[i - 1].y if i > 0 else ctx.y1
         if need_wgrad:
-            ops.conv_wgrad(dz, y_prev, *_grad_buf(conv.weight))
+            ctx.keep.append(dz)
+            with ops.wgrad_side():
+                ops.conv_wgrad(dz, y_prev, *_grad_buf(conv.weight))
         _, wu = pk.get(conv.weight, True, True)
         # the gradient reaching conv1's output also takes conv1's LeakyReLU derivative (fused in the epilogue)
         dy = ops.conv_up(dz, wu, mask=ctx.y1 if i == 0 else None, slope=LRELU_SLOPE)
@@ -326,7 +333,7 @@ class Discriminator(nn.Module):
 # Generator
 # ---------------------------------------------------------------------------------------------
 class _GenCtx:
-    __slots__ = ("xp", "y1", "enc", "head", "dec0", "dec", "out", "B", "shape")
+    __slots__ = ("xp", "y1", "enc", "head", "dec0", "dec", "out", "B", "shape", "keep")
 
 
 def _gen_layers(mod):
@@ -349,6 +356,7 @@ def generator_forward(mod, x, save=True):
     pk = mod._packed
     enc_convs, enc_bns, head_conv, head_bn, dec_convs, dec_bns = _gen_layers(mod)
     ctx = _GenCtx()
+    ctx.keep = []
     bump = _bump_counters(mod, training)
     xp = ops.img_pad_nhwc4(x)
     ctx.B, ctx.xp, ctx.shape = B, (xp if save else None), x.shape
@@ -392,7 +400,9 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
     last = dec_convs[-1]
     dpre = ops.img_pad_nhwc4(dout.contiguous(), yimg=ctx.out)      # d(loss)/d(pre-sigmoid), padded NHWC4 bf16
     if need_wgrad:
-        ops.c3_wgrad_tc(dec_in[-1].y, dpre, *_grad_buf(last.weight))
+        ctx.keep.append(dpre)
+        with ops.wgrad_side():
+            ops.c3_wgrad_tc(dec_in[-1].y, dpre, *_grad_buf(last.weight))
     wc_last, _ = pk.get_c3(last.weight)
     dy = ops.c3_down_tc(dpre, wc_last, ops.ACT_NONE)
     for j in range(len(ctx.dec), 0, -1):
@@ -401,20 +411,26 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
         dz = _bn_act_bwd(dy, sv, bn, ACT_RELU, need_wgrad)
         x_in = dec_in[j - 1].y
         if need_wgrad:
-            ops.conv_wgrad(x_in, dz, *_grad_buf(conv.weight))      # convT wgrad: small = input, big = dz
+            ctx.keep.append(dz)
+            with ops.wgrad_side():
+                ops.conv_wgrad(x_in, dz, *_grad_buf(conv.weight))      # convT wgrad: small = input, big = dz
         wd, _ = pk.get(conv.weight, True, True)
         dy = ops.conv_down(dz, wd)                                      # convT dgrad
     # decoder.0: ConvTranspose2d(100, C, 4, 1, 0)
     dz = _bn_act_bwd(dy, ctx.dec0, dec_bns[0], ACT_RELU, need_wgrad)
     wd0, _ = pk.get(dec_convs[0].weight, True, False)
     if need_wgrad:
-        ops.fc_wgrad(ctx.head.y, dz.view(B, -1), *_grad_buf(dec_convs[0].weight))
+        ctx.keep.append(dz)
+        with ops.wgrad_side():
+            ops.fc_wgrad(ctx.head.y, dz.view(B, -1), *_grad_buf(dec_convs[0].weight))
     dy = ops.fc_down(dz.view(B, -1), wd0.view(wd0.shape[0], -1))
     # encoder head: Conv2d(C, 100, 4, 1, 0)
     dz = _bn_act_bwd(dy, ctx.head, head_bn, ACT_LRELU, need_wgrad)
     y_last = ctx.enc[-1].y
     if need_wgrad:
-        ops.fc_wgrad(dz, y_last.view(B, -1), *_grad_buf(head_conv.weight))
+        ctx.keep.append(dz)
+        with ops.wgrad_side():
+            ops.fc_wgrad(dz, y_last.view(B, -1), *_grad_buf(head_conv.weight))
     wdh, _ = pk.get(head_conv.weight, True, False)
     dy = ops.fc_up(dz, wdh.view(wdh.shape[0], -1)).view(y_last.shape)
     for i in range(len(ctx.enc), 0, -1):
@@ -423,7 +439,9 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
         dz = _bn_act_bwd(dy, sv, bn, ACT_LRELU, need_wgrad)
         y_prev = ctx.enc[i - 2].y if i > 1 else ctx.y1
         if need_wgrad:
-            ops.conv_wgrad(dz, y_prev, *_grad_buf(conv.weight))
+            ctx.keep.append(dz)
+            with ops.wgrad_side():
+                ops.conv_wgrad(dz, y_prev, *_grad_buf(conv.weight))
         _, wu = pk.get(conv.weight, True, True)
         dy = ops.conv_up(dz, wu, mask=ctx.y1 if i == 1 else None, slope=LRELU_SLOPE)
     return _conv1_backward(pk, enc_convs[0].weight, ctx, dy, need_dx, need_wgrad, dx_out, dx_accumulate)

@@ -4,6 +4,8 @@ Every function launches on ``torch.cuda.current_stream()`` and never synchronise
 checked (device, dtype, contiguity) and a wrong argument raises ``ValueError``/``KernelError``
 synchronously -- there is no CPU fallback.
 """
+import contextlib
+
 import torch
 
 from ._lib import KernelError, check, lib
@@ -39,6 +41,28 @@ _lane = 0   # the trainer runs independent sub-chains of the step on two streams
 def set_lane(i):
     global _lane
     _lane = i
+
+
+_wgrad_streams = {}   # lane -> side stream for weight-gradient kernels (set by the trainer for small images)
+
+
+@contextlib.contextmanager
+def wgrad_side():
+    """Run the enclosed weight-gradient kernels on the current lane's side stream, ordered after everything already
+    enqueued on the lane: wgrads only feed the optimiser, so they overlap the dgrad chain that continues on the lane.
+    The caller keeps the operand tensors alive until the streams are joined."""
+    st = _wgrad_streams.get(_lane)
+    if st is None:
+        yield
+        return
+    st.wait_stream(torch.cuda.current_stream())
+    prev = _lane
+    set_lane(prev + 2)
+    try:
+        with torch.cuda.stream(st):
+            yield
+    finally:
+        set_lane(prev)
 
 
 def scratch(kind, nbytes, device):

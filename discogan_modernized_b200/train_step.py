@@ -325,9 +325,15 @@ class DiscoGANTrainer:
         join(4)
 
         red = self.reducer
+        # backward: lanes 0/1 carry the two chains; for small images each chain's weight-gradient kernels go to its
+        # own side stream (lanes 2/3) and overlap the dgrad chain
+        nb = 2
+        if self._side is not None and self.image_size <= 128:
+            ops._wgrad_streams = {0: self._more[0], 1: self._more[1]}
+            nb = 4
         if is_dis:
             stepped = []
-            fork()
+            fork(nb)
             for i, (D, d, c) in enumerate(((D_A, da, co["dis_A"]), (D_B, db, co["dis_B"]))):
                 if c == 0.0:
                     continue
@@ -337,7 +343,7 @@ class DiscoGANTrainer:
                     discriminator_backward(D, d["ctx_r"], dlr, need_dx=False, need_wgrad=True)
                     discriminator_backward(D, d["ctx_f"], dlf, need_dx=False, need_wgrad=True)
                 stepped.append(D)
-            join()
+            join(nb)
             for D in stepped:
                 red.launch(self.flat[D].flat_g)
         else:
@@ -351,7 +357,7 @@ class DiscoGANTrainer:
             for G in stepped:
                 self.flat[G].zero_grad()
             dAB = dBA = None
-            fork()
+            fork(nb)
             # phase A: the discriminators' fake passes, data gradients only  (lane 0: D_B(AB), lane 1: D_A(BA))
             # phase B: the generators' second passes                          (lane 0: G_A(AB)->ABA, lane 1: G_B(BA)->BAB)
             with lane(0):
@@ -368,7 +374,7 @@ class DiscoGANTrainer:
                     dBAB = ops.mse_bwd(BAB, B, co["recon_B"])
                     dBA = generator_backward(G_B, c_gb2, dBAB, need_dx=True, need_wgrad=True, dx_out=dBA,
                                              dx_accumulate=dBA is not None)
-            join(); fork()
+            join(nb); fork(nb)
             # phase C: the generators' first passes (each accumulates into the gradients its second pass just wrote)
             with lane(0):
                 if dAB is not None:
@@ -376,9 +382,10 @@ class DiscoGANTrainer:
             with lane(1):
                 if dBA is not None:
                     generator_backward(G_A, c_ga1, dBA, need_dx=False, need_wgrad=True)
-            join()
+            join(nb)
             for G in stepped:
                 red.launch(self.flat[G].flat_g)
+        ops._wgrad_streams = {}
         red.join()
         fork()
         for i, n in enumerate(stepped):
