@@ -179,22 +179,50 @@ def timed_steps(tr, batches, steps, torch, dist, world):
 
 
 def timed_steps_e2e(tr, host_batches, steps, torch, dist, world):
-    """Public-API loop fed from pinned host memory: H2D of both batches and D2H of the 8 losses every step."""
-    dev_A = torch.empty_like(host_batches[0][0], device="cuda")
-    dev_B = torch.empty_like(host_batches[0][1], device="cuda")
-    host_loss = torch.empty(8, dtype=torch.float32).pin_memory()
+    """Public-API loop fed from pinned host memory.  Every step's two batches are copied host->device inside the timed
+    region (double-buffered on a copy stream, so the copy of step i+1 overlaps the kernels of step i) and every step's
+    eight losses are read back device->host (asynchronously, consumed one step later, as a logging loop would)."""
+    dev = [(torch.empty_like(host_batches[0][0], device="cuda"), torch.empty_like(host_batches[0][1], device="cuda"))
+           for _ in range(2)]
+    host_loss = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    main = torch.cuda.current_stream()
+    seen = 0.0
+
+    def upload(i):
+        slot = i % 2
+        hA, hB = host_batches[i % len(host_batches)]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])           # the step that last read this buffer is done with it
+            dev[slot][0].copy_(hA, non_blocking=True)
+            dev[slot][1].copy_(hB, non_blocking=True)
+            copied[slot].record(copy_stream)
+
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    for ev in consumed:
+        ev.record(main)
     start.record()
+    upload(0)
     for i in range(steps):
-        hA, hB = host_batches[i % len(host_batches)]
-        dev_A.copy_(hA, non_blocking=True)
-        dev_B.copy_(hB, non_blocking=True)
-        tr.step(dev_A, dev_B)
-        host_loss.copy_(tr.loss_buf, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller reads the losses each step
+        slot = i % 2
+        if i + 1 < steps:
+            upload(i + 1)
+        main.wait_event(copied[slot])
+        tr.step(dev[slot][0], dev[slot][1])
+        consumed[slot].record(main)
+        host_loss[slot].copy_(tr.loss_buf, non_blocking=True)
+        loss_ready[slot].record(main)
+        if i > 0:                                            # consume the previous step's losses on the host
+            loss_ready[1 - slot].synchronize()
+            seen += float(host_loss[1 - slot][0])
+    loss_ready[(steps - 1) % 2].synchronize()
+    seen += float(host_loss[(steps - 1) % 2][0])
     end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -204,6 +232,7 @@ def timed_steps_e2e(tr, host_batches, steps, torch, dist, world):
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
+    assert seen == seen, "losses are NaN"
     h2d = 2 * host_batches[0][0].numel() * 4
     return ms, h2d, 32
 

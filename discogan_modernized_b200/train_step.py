@@ -328,7 +328,8 @@ class DiscoGANTrainer:
         # backward: lanes 0/1 carry the two chains; for small images each chain's weight-gradient kernels go to its
         # own side stream (lanes 2/3) and overlap the dgrad chain
         nb = 2
-        if self._side is not None and self.image_size <= 128:
+        wl = os.environ.get("DISCOGAN_B200_WGRAD_LANES", "auto")
+        if self._side is not None and (wl == "1" or (wl == "auto" and self.image_size <= 128)):
             ops._wgrad_streams = {0: self._more[0], 1: self._more[1]}
             nb = 4
         if is_dis:
