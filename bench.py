@@ -260,9 +260,9 @@ def measure_roofline(tr, batches, torch, pk):
 
     def hbm_work(name, a):
         if name == "bn_act_fwd":
-            return "bn_act_fwd", 4.0 * a[0].numel(), ""            # read z, write y (bf16)
-        if name == "bn_act_bwd":
-            return "bn_act_bwd", 10.0 * a[0].numel(), ""           # reduce: dy,z ; dx: dy,z + write dz (bf16)
+            return "bn_act_fwd", 4.0 * a[0].numel(), f"bn_fwd {a[0].shape[0]}x{a[0].shape[1]}"   # read z, write y (bf16)
+        if name == "bn_act_bwd":                                   # reduce: dy,z ; dx: dy,z + write dz (bf16)
+            return "bn_act_bwd", 10.0 * a[0].numel(), f"bn_bwd {a[0].shape[0]}x{a[0].shape[1]}"
         return "adam", 28.0 * a[0].numel(), ""                     # p,g,m,v read + p,m,v write (fp32); +repack excluded
 
     names = {n: conv_work for n in ("conv_down", "conv_up", "conv_wgrad", "conv_down_stats", "conv_up_stats")}
@@ -312,8 +312,10 @@ def measure_roofline(tr, batches, torch, pk):
         else:
             out[cls] = {"launches": n, "gbs": amount / sec / 1e9, "avg_us": sec / n * 1e6, "ms_per_cycle": sec * 1e3,
                         "frac_of_hbm_peak": amount / sec / 1e9 / pk["hbm"]}
-    top = sorted(layers.items(), key=lambda kv: -kv[1][1])[:12]
-    out["layers"] = {k: {"launches": n, "tflops": round(a / sec / 1e12, 1), "ms_per_cycle": round(sec * 1e3, 3)}
+    top = sorted(layers.items(), key=lambda kv: -kv[1][1])[:16]
+    out["layers"] = {k: ({"launches": n, "gbs": round(a / sec / 1e9, 1), "ms_per_cycle": round(sec * 1e3, 3)}
+                         if k.startswith("bn_") else
+                         {"launches": n, "tflops": round(a / sec / 1e12, 1), "ms_per_cycle": round(sec * 1e3, 3)})
                      for k, (a, sec, n) in top}
     g = by.get("conv_gemm", [0.0, 1.0, 1])
     ach = g[0] / g[1] / 1e12
