@@ -172,3 +172,57 @@ def test_golden_family64(golden_dir):
         for k, v in g["logs"][it].items():
             if k in got:
                 assert abs(got[k] - v) <= 0.05 * abs(v) + 0.02, (it, k, got[k], v)
+
+
+def test_full_size_512_step_matches_oracle():
+    """BASELINE's full-size topology (512x512, the reference model.py itself), B=2: one D step and one G step of the
+    fused trainer against the oracle on the same device -- exercises the 2048-channel layers, the direct wgrad
+    epilogue and the deep split-free GEMMs that the 64x64 family never reaches."""
+    from discogan_modernized_b200 import DiscoGANTrainer, model
+    from oracle.step import OracleStep, build_nets, synthetic_batch
+    S, B = 512, 2
+    ref_nets = build_nets(S, seed=1234, device="cuda")
+    nets = []
+    with torch.device("meta"):
+        shells = [model.Generator(True, S), model.Generator(True, S), model.Discriminator(S), model.Discriminator(S)]
+    for shell, r in zip(shells, ref_nets):
+        n = shell.to_empty(device="cuda")
+        n.load_state_dict(r.state_dict())
+        nets.append(n)
+    tr = DiscoGANTrainer(image_size=S, nets=nets)
+    ref = OracleStep(ref_nets, device="cuda")
+    for it in range(2):
+        A, Bt = synthetic_batch(B, S, step=it, device="cuda")
+        tr.step(A, Bt)
+        want = ref.step(A, Bt)
+        got = tr.losses()
+        for k, v in got.items():
+            assert abs(v - want[k]) <= 0.06 * abs(want[k]) + 0.03, (it, k, v, want[k])
+    a = dict(tr.D_A.named_parameters())["conv7.weight"]
+    b = dict(ref_nets[2].named_parameters())["conv7.weight"]
+    assert rel_l2(a, b) < 0.05
+    tr.close()
+
+
+def test_full_size_512_generator_forward():
+    """Generator forward at 512x512 against the golden minted from the REFERENCE model.py on CPU
+    (tests/golden/ref512_forward.pt): same seed-1234 construction order, same synthetic batch."""
+    from pathlib import Path
+    from discogan_modernized_b200 import model
+    from oracle.step import synthetic_batch
+    g = torch.load(Path(__file__).resolve().parent / "golden" / "ref512_forward.pt")
+    torch.manual_seed(1234)
+    G = model.Generator(extra_layers=True)            # default image_size = 512
+    D = model.Discriminator()
+    G, D = G.cuda(), D.cuda()
+    A, Bt = synthetic_batch(2, 512, step=0, device="cuda")
+    with torch.no_grad():
+        y = G(A)
+        p, feats = D(Bt)
+    got = y.flatten().cpu()[g["G_out_idx"]]
+    assert float((got - g["G_out_samples"]).abs().max()) < 3e-2       # sigmoid outputs in (0,1), bf16 chain
+    assert abs(float(y.mean()) - float(g["G_out_mean"])) < 5e-3
+    assert torch.allclose(p.flatten().cpu(), g["D_prob"], atol=3e-2)
+    assert [list(f.shape) for f in feats] == g["feat_shapes"]
+    assert torch.allclose(torch.stack([f.mean() for f in feats]).cpu(), g["feat_means"], rtol=5e-2, atol=5e-3)
+    assert torch.allclose(G.state_dict()["encoder.3.running_mean"].cpu(), g["G_running_mean_3"], rtol=5e-2, atol=1e-3)
