@@ -350,6 +350,7 @@ struct WgradParams {
   float* dw;  // direct mode (splits == 1): the epilogue writes dw = beta*dw + acc in PyTorch layout itself
   float beta;
   int direct;
+  int debug;  // timing experiments only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
   int share;  // 0: one TMA box per tap.  1/2: taps that differ by a one-pixel shift inside the same parity plane share a
               // 33-pixel box and are addressed with a 128-byte row offset (1: descriptor base_offset = row phase, 2: 0)
 };
@@ -409,6 +410,14 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = smem + stage * kWgStageBytes;
         uint8_t* sb = sa + 2 * kWgBoxBytes;
+        if (p.debug == 2) {
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == kWgStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          continue;
+        }
         mbar_arrive_expect_tx(&full_bar[stage],
                               p.share ? (uint32_t)(2 * kWgBoxBytes + 4 * 33 * 128) : (uint32_t)kWgStageBytes);
         tma_load_4d(sa, &tmS, &full_bar[stage], mt * 128, w0, h0, b0);
@@ -452,6 +461,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
         const uint32_t sb = sa + 2 * kWgBoxBytes;
 #pragma unroll
         for (int ks = 0; ks < kWgKC / 16; ++ks) {
+          if (p.debug == 1 && ch > chunk_begin) break;
           const uint32_t accum = (ch > chunk_begin || ks > 0) ? 1u : 0u;
           // MN-major SW128: LBO = distance between 64-wide MN blocks, SBO = distance between 8-row K groups
           const uint64_t da = desc_base | (uint64_t)(((sa + ks * 2048) & 0x3FFFFu) >> 4);
@@ -684,7 +694,9 @@ void wgrad_plan(int B, int Hs, int Ws, int Cs, int Cb, WgradParams* p) {
   p->m_tiles = Cs / 128;
   p->n_tiles = Cb / 64;
   const int work = p->m_tiles * p->n_tiles * 2;
-  int splits = dg_ceil_div(2 * num_sms(), work);
+  // one CTA per SM (200 KB of smem): aim for a single full wave -- work*splits <= #SMs -- instead of 2+ partial waves,
+  // which also halves the split-K partial traffic
+  int splits = work >= num_sms() ? 1 : num_sms() / work;
   const int max_splits = p->total_chunks / 16;  // at least 16 K-chunks (512 pixels) per split: keeps the
   if (splits > max_splits) splits = max_splits;  // workspace traffic below the operand traffic on small layers
   if (splits < 1) splits = 1;
@@ -783,6 +795,12 @@ int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta
     share_mode = e ? atoi(e) : 0;
   }
   p.share = (share_mode > 0 && p.Wt == 32 && p.Ht == 1 && p.Bt == 1) ? 2 : 0;
+  static int debug_mode = -1;
+  if (debug_mode < 0) {
+    const char* e = getenv("DG_WGRAD_DEBUG");
+    debug_mode = e ? atoi(e) : 0;
+  }
+  p.debug = debug_mode;
   CUtensorMap tmS, tmBig, tmBig33;
   int rc = make_nhwc_map(&tmS, small, B, Hs, Ws, Cs, p.Wt, p.Ht, p.Bt);
   if (rc) return rc;
