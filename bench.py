@@ -243,7 +243,7 @@ def measure_roofline(tr, batches, torch, pk):
     FLOPs 2*B*Ho*Wo*Co*Ci*16 per launch.  HBM-bound: BatchNorm(+activation) forward/backward and Adam, algorithmic
     bytes per DESIGN.md section 3.4."""
     from discogan_modernized_b200 import ops
-    recs = []
+    recs, calls = [], []
 
     def conv_work(name, a):
         if name in ("conv_down", "conv_down_stats"):
@@ -277,6 +277,8 @@ def measure_roofline(tr, batches, torch, pk):
             e.record()
             cls, amount, label = work(name, a)
             recs.append((cls, amount, label, s, e))
+            if cls.startswith("conv"):
+                calls.append((cls, amount, fn, a, k))      # arguments kept alive for the back-to-back replay below
             return out
         return inner
 
@@ -288,6 +290,7 @@ def measure_roofline(tr, batches, torch, pk):
     try:
         for cycle in range(2):                 # first cycle: untimed, lets the caching allocator grow its eager pool
             recs.clear()                       # (cudaMalloc stalls between the events would be charged to kernels)
+            calls.clear()
             for i in range(3):
                 A, B = batches[i % len(batches)]
                 tr.step(A, B)
@@ -296,6 +299,33 @@ def measure_roofline(tr, batches, torch, pk):
         tr.use_graphs, tr._side = saved_graphs, saved_side
         for n, f in orig.items():
             setattr(ops, n, f)
+    # Eager per-launch events include host launch gaps whenever the GPU is faster than Python (always at 64x64).  So the
+    # tensor-core kernels are timed a second time: exactly the cycle's launches of one kernel, same arguments, captured
+    # into a CUDA graph and replayed back to back between two events (no host gaps, nothing else on the GPU).
+    replay = {}
+    for cls in ("conv_gemm", "conv_wgrad"):
+        mine = [c for c in calls if c[0] == cls]
+        if not mine:
+            continue
+        try:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                keep = [fn(*a, **k) for _, _, fn, a, k in mine]
+            g.replay()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(3):
+                g.replay()
+            e.record()
+            torch.cuda.synchronize()
+            replay[cls] = (sum(c[1] for c in mine), s.elapsed_time(e) * 1e-3 / 3, len(mine))
+            del g, keep
+        except Exception as ex:  # noqa: BLE001
+            replay[cls] = None
+            print(f"bench: graph replay timing of {cls} failed: {ex}", file=sys.stderr)
+    calls.clear()
     by, layers = {}, {}
     for cls, amount, label, s, e in recs:
         sec = s.elapsed_time(e) * 1e-3
@@ -317,7 +347,18 @@ def measure_roofline(tr, batches, torch, pk):
                          if k.startswith("bn_") else
                          {"launches": n, "tflops": round(a / sec / 1e12, 1), "ms_per_cycle": round(sec * 1e3, 3)})
                      for k, (a, sec, n) in top}
+    for cls, r in replay.items():
+        if r:
+            out[cls]["replay_tflops"] = r[0] / r[1] / 1e12
+            out[cls]["replay_avg_us"] = r[1] / r[2] * 1e6
     g = by.get("conv_gemm", [0.0, 1.0, 1])
+    timing = "per-launch CUDA events, eager launches"
+    peak, peak_src = pk["tf_sustained"], f"{pk['src']} bf16 sustained (kernel timed inside the step)"
+    if replay.get("conv_gemm"):
+        g = list(replay["conv_gemm"])
+        timing = "CUDA events around a back-to-back graph replay of the cycle's launches of this kernel"
+        if 3 * g[1] < 0.25:      # a burst of well under a second: compare with the burst figure
+            peak, peak_src = pk["tf_burst"], f"{pk['src']} bf16 burst (kernel timed alone, {3 * g[1] * 1e3:.0f} ms of launches)"
     ach = g[0] / g[1] / 1e12
     # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel (profiles/README.md); only the
     # 512^2 B=32 workload has been captured so far
@@ -327,10 +368,10 @@ def measure_roofline(tr, batches, torch, pk):
     if tfile.exists() and big.shape[-1] == 512 and big.shape[0] == 32:
         traffic = json.loads(tfile.read_text())["conv_gemm_kernel"]["dram_bytes_per_launch"]
     roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: conv fprop/dgrad, convT fprop/dgrad)",
-            "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-            "peak_source": f"{pk['src']} bf16 sustained (kernel timed inside the step)", "traffic": traffic,
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_source": peak_src, "traffic": traffic,
             "launches_per_cycle": g[2], "avg_launch_us": g[1] / max(g[2], 1) * 1e6,
-            "algorithmic": "2*B*Ho*Wo*Co*Ci*16 FLOP per launch"}
+            "algorithmic": "2*B*Ho*Wo*Co*Ci*16 FLOP per launch", "timing": timing}
     return roof, out
 
 
