@@ -357,7 +357,7 @@ def measure_roofline(tr, batches, torch, pk):
     if replay.get("conv_gemm"):
         g = list(replay["conv_gemm"])
         timing = "CUDA events around a back-to-back graph replay of the cycle's launches of this kernel"
-        if 3 * g[1] < 0.25:      # a burst of well under a second: compare with the burst figure
+        if 3 * g[1] < 0.02:      # a burst of a few milliseconds: compare with the burst figure
             peak, peak_src = pk["tf_burst"], f"{pk['src']} bf16 burst (kernel timed alone, {3 * g[1] * 1e3:.0f} ms of launches)"
     ach = g[0] / g[1] / 1e12
     # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel (profiles/README.md); only the
