@@ -306,7 +306,8 @@ fc_up_kernel(const TS* __restrict__ small, const bf16* __restrict__ wd, bf16* __
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
-  for (int n = 0; n < Ns; ++n) {
+#pragma unroll 8
+  for (int n = 0; n < Ns; ++n) {   // unrolled: 8 weight rows in flight (the loop is load-latency bound)
     float wv[8];
     unpack8(*reinterpret_cast<const bf16x8*>(wd + (size_t)n * K + k), wv);
 #pragma unroll
@@ -338,7 +339,7 @@ fc_wgrad_kernel(const TS* __restrict__ small, const bf16* __restrict__ big, floa
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   const bf16* bp = big + (size_t)tap * C + c0;
-#pragma unroll 4
+#pragma unroll 8
   for (int b = 0; b < B; ++b) {
     const float s = ld_small<TS>(small + (size_t)b * Ns + n);
     float f[8];
