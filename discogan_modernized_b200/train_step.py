@@ -305,10 +305,36 @@ class DiscoGANTrainer:
             AB, c_gb1 = generator_forward(G_B, A, save=save_g)       # A -> B
         with lane(1):
             BA, c_ga1 = generator_forward(G_A, B, save=save_g)       # B -> A
+        # On a D step the discriminators' backward passes need nothing from the generators' second passes (the BCE
+        # gradient of the real logit depends on the real pass only), so each pass is back-propagated on its lane right
+        # after its forward, in the reference's accumulation order (real, then fake), beside the generator forwards.
+        d_coef = {0: co["dis_A"], 1: co["dis_B"]}
+        stepped = []
+        if is_dis:
+            for D, c in ((D_A, co["dis_A"]), (D_B, co["dis_B"])):
+                if c != 0.0:
+                    self.flat[D].zero_grad()
+                    stepped.append(D)
+
+        def real_pass(D, img, slot):
+            real = discriminator_forward(D, img, save=is_dis)
+            if is_dis and d_coef[slot] != 0.0:
+                p_real = ops.sigmoid_fwd(real[0])
+                dlr, _ = ops.gan_bce_bwd(p_real, p_real, d_coef[slot], 0.0, want_fake=False)
+                discriminator_backward(D, real[2], dlr, need_dx=False, need_wgrad=True)
+            return real
+
+        def fake_pass(D, real, img, slot):
+            d = self._disc_fake_and_losses(D, real, img, slot)
+            if is_dis and d_coef[slot] != 0.0:
+                _, dlf = ops.gan_bce_bwd(d["p_real"], d["p_fake"], d_coef[slot], 0.0, want_real=False)
+                discriminator_backward(D, d["ctx_f"], dlf, need_dx=False, need_wgrad=True)
+            return d
+
         with lane(l2):
-            real_a = discriminator_forward(D_A, A, save=is_dis)
+            real_a = real_pass(D_A, A, 0)
         with lane(l3):
-            real_b = discriminator_forward(D_B, B, save=is_dis)
+            real_b = real_pass(D_B, B, 1)
         join(4); fork(4)
         # phase 2: second generator passes + reconstruction losses, fake discriminator passes + GAN / FM losses
         # (every network's second pass follows its first: BatchNorm running statistics advance in reference order)
@@ -319,9 +345,9 @@ class DiscoGANTrainer:
             BAB, c_gb2 = generator_forward(G_B, BA, save=save_g)     # B -> A -> B
             ops.mse_fwd(BAB, B, self.loss_buf[7:8])
         with lane(l2):
-            da = self._disc_fake_and_losses(D_A, real_a, BA, 0)
+            da = fake_pass(D_A, real_a, BA, 0)
         with lane(l3):
-            db = self._disc_fake_and_losses(D_B, real_b, AB, 1)
+            db = fake_pass(D_B, real_b, AB, 1)
         join(4)
 
         red = self.reducer
@@ -333,24 +359,11 @@ class DiscoGANTrainer:
             ops._wgrad_streams = {0: self._more[0], 1: self._more[1]}
             nb = 4
         if is_dis:
-            stepped = []
-            fork(nb)
-            for i, (D, d, c) in enumerate(((D_A, da, co["dis_A"]), (D_B, db, co["dis_B"]))):
-                if c == 0.0:
-                    continue
-                self.flat[D].zero_grad()
-                with lane(i):
-                    dlr, dlf = ops.gan_bce_bwd(d["p_real"], d["p_fake"], c, 0.0)
-                    discriminator_backward(D, d["ctx_r"], dlr, need_dx=False, need_wgrad=True)
-                    discriminator_backward(D, d["ctx_f"], dlf, need_dx=False, need_wgrad=True)
-                stepped.append(D)
-            join(nb)
-            for D in stepped:
+            for D in stepped:                                    # backward already done beside the forward passes
                 red.launch(self.flat[D].flat_g)
         else:
             use_a = co["gen_A"] != 0.0 or co["fm_A"] != 0.0      # losses through D_A(BA): reach G_A pass 1
             use_b = co["gen_B"] != 0.0 or co["fm_B"] != 0.0      # losses through D_B(AB): reach G_B pass 1
-            stepped = []
             if use_b or co["recon_A"] != 0.0 or co["recon_B"] != 0.0:
                 stepped.append(G_B)
             if use_a or co["recon_B"] != 0.0 or co["recon_A"] != 0.0:
