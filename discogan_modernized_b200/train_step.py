@@ -197,7 +197,7 @@ class DiscoGANTrainer:
         self._scratch_gen = -1
         use_lanes = os.environ.get("DISCOGAN_B200_LANES", "1") != "0"
         self._side = torch.cuda.Stream(device=self.device) if use_lanes else None          # lane 1
-        self._more = [torch.cuda.Stream(device=self.device) for _ in range(2)] if use_lanes else []   # lanes 2, 3
+        self._more = [torch.cuda.Stream(device=self.device) for _ in range(4)] if use_lanes else []   # lanes 2..5
         self._graph_launches = {}   # kernels inside each captured graph
         self.kernel_launches = 0    # kernels of this library launched (eagerly or by graph replay) by step()
 
@@ -299,8 +299,13 @@ class DiscoGANTrainer:
         lane, fork, join = self._lane, self._fork, self._join
         # forward, phase 1 (4 lanes): the two first generator passes and the two real discriminator passes
         # (big images fill the GPU with single kernels: the discriminators then share lanes 0/1 with the generators)
-        l2, l3 = (2, 3) if self.image_size <= 128 else (0, 1)
-        fork(4)
+        small = self._side is not None and self.image_size <= 128
+        l2, l3 = (2, 3) if small else (0, 1)
+        nf = 4
+        if small and is_dis:     # the discriminators' early backward: weight gradients on lanes 4/5
+            ops._wgrad_streams = {2: self._more[2], 3: self._more[3]}
+            nf = 6
+        fork(nf)
         with lane(0):
             AB, c_gb1 = generator_forward(G_B, A, save=save_g)       # A -> B
         with lane(1):
@@ -335,7 +340,7 @@ class DiscoGANTrainer:
             real_a = real_pass(D_A, A, 0)
         with lane(l3):
             real_b = real_pass(D_B, B, 1)
-        join(4); fork(4)
+        join(nf); fork(nf)
         # phase 2: second generator passes + reconstruction losses, fake discriminator passes + GAN / FM losses
         # (every network's second pass follows its first: BatchNorm running statistics advance in reference order)
         with lane(0):
@@ -348,7 +353,8 @@ class DiscoGANTrainer:
             da = fake_pass(D_A, real_a, BA, 0)
         with lane(l3):
             db = fake_pass(D_B, real_b, AB, 1)
-        join(4)
+        join(nf)
+        ops._wgrad_streams = {}
 
         red = self.reducer
         # backward: lanes 0/1 carry the two chains; for small images each chain's weight-gradient kernels go to its
