@@ -27,8 +27,8 @@ constexpr uint32_t kSw32 = 6;  // UMMA layout type SWIZZLE_32B
 // fp32 NCHW image (optionally * y(1-y)) -> zero-padded NHWC4 bf16 [B][S+2][S+2][4]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-img_pad_nhwc4_kernel(const float* __restrict__ img, const float* __restrict__ yimg, bf16* __restrict__ out, int B,
-                     int S) {
+img_pad_nhwc4_kernel(const float* __restrict__ img, const float* __restrict__ img2, const float* __restrict__ yimg,
+                     bf16* __restrict__ out, int B, int S) {
   const int Sp = S + 2;
   const long long total = (long long)B * Sp * Sp;
   const size_t plane = (size_t)S * S;
@@ -43,6 +43,7 @@ img_pad_nhwc4_kernel(const float* __restrict__ img, const float* __restrict__ yi
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float t = img[off + c * plane];
+        if (img2) t += img2[off + c * plane];      // two gradient contributions summed on the fly
         if (yimg) {
           const float s = yimg[off + c * plane];
           t *= s * (1.f - s);
@@ -373,13 +374,15 @@ int dg_c3_pack_weights(const float* w, void* wc, void* wu3, cudaStream_t stream)
   return DG_OK;
 }
 
-// fp32 NCHW [B,3,S,S] (times yimg*(1-yimg) when yimg != NULL) -> bf16 [B,S+2,S+2,4], zero border and 4th channel
-int dg_img_pad_nhwc4(const float* img, const float* yimg, void* out, int B, int S, cudaStream_t stream) {
+// fp32 NCHW [B,3,S,S] (+ img2 when != NULL) (times yimg*(1-yimg) when yimg != NULL) -> bf16 [B,S+2,S+2,4], zero
+// border and 4th channel
+int dg_img_pad_nhwc4(const float* img, const float* img2, const float* yimg, void* out, int B, int S,
+                     cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && S >= 4 && img && out, "img_pad_nhwc4: bad args");
   const long long total = (long long)B * (S + 2) * (S + 2);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  img_pad_nhwc4_kernel<<<(int)blocks, 256, 0, stream>>>(img, yimg, (bf16*)out, B, S);
+  img_pad_nhwc4_kernel<<<(int)blocks, 256, 0, stream>>>(img, img2, yimg, (bf16*)out, B, S);
   DG_CHECK_LAUNCH("img_pad_nhwc4");
   return DG_OK;
 }

@@ -391,14 +391,14 @@ def generator_forward(mod, x, save=True):
     return out, ctx
 
 
-def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=None, dx_accumulate=False):
-    """dout: d(loss)/d(output image), fp32 NCHW.  Returns d(loss)/d(input image) or None."""
+def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=None, dx_accumulate=False, dout2=None):
+    """dout (+ dout2): d(loss)/d(output image), fp32 NCHW.  Returns d(loss)/d(input image) or None."""
     pk = mod._packed
     B = ctx.B
     enc_convs, enc_bns, head_conv, head_bn, dec_convs, dec_bns = _gen_layers(mod)
     dec_in = [ctx.dec0] + ctx.dec          # dec_in[j].y is the input of dec_convs[j+1]
     last = dec_convs[-1]
-    dpre = ops.img_pad_nhwc4(dout.contiguous(), yimg=ctx.out)      # d(loss)/d(pre-sigmoid), padded NHWC4 bf16
+    dpre = ops.img_pad_nhwc4(dout.contiguous(), yimg=ctx.out, img2=dout2)   # d(loss)/d(pre-sigmoid), padded NHWC4 bf16
     if need_wgrad:
         ctx.keep.append(dpre)
         with ops.wgrad_side():

@@ -43,7 +43,7 @@ def set_lane(i):
     _lane = i
 
 
-_wgrad_streams = {}   # lane -> side stream for weight-gradient kernels (set by the trainer for small images)
+_wgrad_streams = {}   # lane -> (side stream, its lane id) for weight-gradient kernels (set by the trainer, small images)
 
 
 @contextlib.contextmanager
@@ -51,13 +51,14 @@ def wgrad_side():
     """Run the enclosed weight-gradient kernels on the current lane's side stream, ordered after everything already
     enqueued on the lane: wgrads only feed the optimiser, so they overlap the dgrad chain that continues on the lane.
     The caller keeps the operand tensors alive until the streams are joined."""
-    st = _wgrad_streams.get(_lane)
-    if st is None:
+    ent = _wgrad_streams.get(_lane)
+    if ent is None:
         yield
         return
+    st, side_lane = ent                      # (stream, scratch lane id of that stream)
     st.wait_stream(torch.cuda.current_stream())
     prev = _lane
-    set_lane(prev + 2)
+    set_lane(side_lane)
     try:
         with torch.cuda.stream(st):
             yield
@@ -214,12 +215,12 @@ def c3_pack_weights(w, out=None):
     return wc, wu3
 
 
-def img_pad_nhwc4(img, yimg=None):
-    """fp32 NCHW [B,3,S,S] (times yimg*(1-yimg) if given) -> zero-padded bf16 NHWC4 [B,S+2,S+2,4]."""
+def img_pad_nhwc4(img, yimg=None, img2=None):
+    """fp32 NCHW [B,3,S,S] (+ img2) (times yimg*(1-yimg) if given) -> zero-padded bf16 NHWC4 [B,S+2,S+2,4]."""
     B, _, S, _ = img.shape
     out = torch.empty(B, S + 2, S + 2, 4, dtype=BF16, device=img.device)
-    check(lib().dg_img_pad_nhwc4(_ptr(img, F32, "img"), _ptr(yimg, F32, "yimg"), _ptr(out), B, S, _stream()),
-          "dg_img_pad_nhwc4")
+    check(lib().dg_img_pad_nhwc4(_ptr(img, F32, "img"), _ptr(img2, F32, "img2"), _ptr(yimg, F32, "yimg"), _ptr(out), B, S,
+                                 _stream()), "dg_img_pad_nhwc4")
     return out
 
 

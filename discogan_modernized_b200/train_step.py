@@ -303,7 +303,7 @@ class DiscoGANTrainer:
         l2, l3 = (2, 3) if small else (0, 1)
         nf = 4
         if small and is_dis:     # the discriminators' early backward: weight gradients on lanes 4/5
-            ops._wgrad_streams = {2: self._more[2], 3: self._more[3]}
+            ops._wgrad_streams = {2: (self._more[2], 4), 3: (self._more[3], 5)}
             nf = 6
         fork(nf)
         with lane(0):
@@ -362,8 +362,9 @@ class DiscoGANTrainer:
         nb = 2
         wl = os.environ.get("DISCOGAN_B200_WGRAD_LANES", "auto")
         if self._side is not None and (wl == "1" or (wl == "auto" and self.image_size <= 128)):
-            ops._wgrad_streams = {0: self._more[0], 1: self._more[1]}
-            nb = 4
+            # (lanes 2/3 carry the discriminators' fake-pass backward at the same time, hence lanes 4/5 here)
+            ops._wgrad_streams = {0: (self._more[2], 4), 1: (self._more[3], 5)}
+            nb = 6
         if is_dis:
             for D in stepped:                                    # backward already done beside the forward passes
                 red.launch(self.flat[D].flat_g)
@@ -376,32 +377,36 @@ class DiscoGANTrainer:
                 stepped.append(G_A)
             for G in stepped:
                 self.flat[G].zero_grad()
-            dAB = dBA = None
-            fork(nb)
-            # phase A: the discriminators' fake passes, data gradients only  (lane 0: D_B(AB), lane 1: D_A(BA))
-            # phase B: the generators' second passes                          (lane 0: G_A(AB)->ABA, lane 1: G_B(BA)->BAB)
-            with lane(0):
+            dAB = dBA = dAB_d = dBA_d = None
+            fork(6 if small else nb)
+            # phase A (lanes 2/3 for small images): the discriminators' fake passes, data gradients only -- independent of
+            # phase B (lanes 0/1): the generators' second passes.  Both produce a gradient for AB (resp. BA); the two
+            # are summed on the fly by the first kernel of phase C.
+            la, lb = (2, 3) if small else (0, 1)
+            with lane(la):
                 if use_b:
-                    dAB = self._disc_fake_backward(D_B, db, co["gen_B"], co["fm_B"], AB.shape[0])
+                    dAB_d = self._disc_fake_backward(D_B, db, co["gen_B"], co["fm_B"], AB.shape[0])
+            with lane(lb):
+                if use_a:
+                    dBA_d = self._disc_fake_backward(D_A, da, co["gen_A"], co["fm_A"], BA.shape[0])
+            with lane(0):
                 if co["recon_A"] != 0.0:
                     dABA = ops.mse_bwd(ABA, A, co["recon_A"])
-                    dAB = generator_backward(G_A, c_ga2, dABA, need_dx=True, need_wgrad=True, dx_out=dAB,
-                                             dx_accumulate=dAB is not None)
+                    dAB = generator_backward(G_A, c_ga2, dABA, need_dx=True, need_wgrad=True)
             with lane(1):
-                if use_a:
-                    dBA = self._disc_fake_backward(D_A, da, co["gen_A"], co["fm_A"], BA.shape[0])
                 if co["recon_B"] != 0.0:
                     dBAB = ops.mse_bwd(BAB, B, co["recon_B"])
-                    dBA = generator_backward(G_B, c_gb2, dBAB, need_dx=True, need_wgrad=True, dx_out=dBA,
-                                             dx_accumulate=dBA is not None)
-            join(nb); fork(nb)
+                    dBA = generator_backward(G_B, c_gb2, dBAB, need_dx=True, need_wgrad=True)
+            join(6 if small else nb); fork(nb)
             # phase C: the generators' first passes (each accumulates into the gradients its second pass just wrote)
             with lane(0):
-                if dAB is not None:
-                    generator_backward(G_B, c_gb1, dAB, need_dx=False, need_wgrad=True)
+                g1, g2 = (dAB, dAB_d) if dAB is not None else (dAB_d, None)
+                if g1 is not None:
+                    generator_backward(G_B, c_gb1, g1, need_dx=False, need_wgrad=True, dout2=g2)
             with lane(1):
-                if dBA is not None:
-                    generator_backward(G_A, c_ga1, dBA, need_dx=False, need_wgrad=True)
+                g1, g2 = (dBA, dBA_d) if dBA is not None else (dBA_d, None)
+                if g1 is not None:
+                    generator_backward(G_A, c_ga1, g1, need_dx=False, need_wgrad=True, dout2=g2)
             join(nb)
             for G in stepped:
                 red.launch(self.flat[G].flat_g)

@@ -87,7 +87,8 @@ int dg_convT_c3_out_bwd(const void* x, const float* w, const float* y, const flo
  * image [B,S+2,S+2,4] (optionally multiplied by y(1-y), the Sigmoid derivative); weights: wc bf16 [64][64],
  * wu3 bf16 [16][16][64] from dg_c3_pack_weights */
 int dg_c3_pack_weights(const float* w, void* wc, void* wu3, dg_stream_t stream);
-int dg_img_pad_nhwc4(const float* img, const float* yimg, void* out, int B, int S, dg_stream_t stream);
+int dg_img_pad_nhwc4(const float* img, const float* img2 /* optional, added */, const float* yimg, void* out, int B,
+                     int S, dg_stream_t stream);
 int dg_c3_down_tc(const void* xp, const void* wc, void* y, int B, int S, int act, float slope, dg_stream_t stream);
 int dg_c3_up_tc(const void* x64, const void* wu3, float* img, int B, int S, int sigmoid, int accumulate,
                 dg_stream_t stream);

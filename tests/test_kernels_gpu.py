@@ -341,6 +341,8 @@ def test_c3_tc_down_up_wgrad(B, S):
     yimg = torch.rand(B, 3, S, S, device="cuda", generator=gen)
     dpre = (x * yimg * (1 - yimg)).to(BF16).float()
     dp = ops.img_pad_nhwc4(x, yimg)
+    half = 0.5 * x
+    assert torch.equal(ops.img_pad_nhwc4(half, yimg, img2=half), dp)          # two summed gradient contributions
     ref2 = F.conv2d(dpre, wq, stride=2, padding=1)
     assert rel_l2(to_nchw_f32(ops.c3_down_tc(dp, wc, 0)), ref2) < 4e-3
     # up: last ConvTranspose2d forward (+sigmoid) and accumulate mode
