@@ -54,6 +54,8 @@ struct ConvGemmParams {
   int img_sigmoid, img_accumulate;
   float* stat_part;   // BatchNorm statistics fused in the epilogue: per-CTA partial sums [2][gridDim.x][N] of the fp32
                       // accumulators (sum, sum of squares) over the rows this CTA produced; NULL = off
+  int splits, kps;    // split-K: work item = (tile, split); a split covers K-iterations [split*kps, (split+1)*kps)
+  float* ws;          // split-K: fp32 [output pixels][N] accumulator (zeroed by the launcher), NULL when splits == 1
 };
 
 // Sum the 32 values each lane holds for 32 columns over the 32 lanes (rows) of the warp: afterwards v[0] of lane l is
@@ -135,10 +137,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int w = blockIdx.x; w < p.num_tiles * p.splits; w += gridDim.x) {
+        const TileCoord t = decode_tile(p, w % p.num_tiles);
+        const int k_begin = (w / p.num_tiles) * p.kps, k_end = min(p.k_iters, k_begin + p.kps);
         const int py = t.par >> 1, px = t.par & 1;
-        for (int it = 0; it < p.k_iters; ++it) {
+        for (int it = k_begin; it < k_end; ++it) {
           const int tap_i = it / p.cpk;
           const int c0 = (it - tap_i * p.cpk) * kBlockK;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -178,11 +181,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < p.num_tiles * p.splits; w += gridDim.x) {
+        const int k_begin = (w / p.num_tiles) * p.kps, k_end = min(p.k_iters, k_begin + p.kps);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
-        for (int it = 0; it < p.k_iters; ++it) {
+        for (int it = k_begin; it < k_end; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem0 + (uint32_t)(stage * stage_bytes);
@@ -190,7 +194,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t db0 = desc_base | (uint64_t)(((sa + kATileBytes) & 0x3FFFFu) >> 4);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(d_tmem, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (it > k_begin || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == p.num_stages) {
             stage = 0;
@@ -212,8 +216,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = threadIdx.x - 64; i < 2 * p.N; i += 128) s_stat[i] = 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int w = blockIdx.x; w < p.num_tiles * p.splits; w += gridDim.x) {
+      const TileCoord t = decode_tile(p, w % p.num_tiles);
       const int wl = row % p.Wt;
       const int hl = (row / p.Wt) % p.Ht;
       const int bl = row / (p.Wt * p.Ht);
@@ -246,7 +250,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
-      if (p.img != nullptr) {
+      if (p.ws != nullptr) {
+        // split-K: accumulate this split's partial tile into the fp32 workspace with 16-byte vector reductions
+        float* wrow = p.ws + opix * p.N + (size_t)t.nt * p.block_n;
+        for (int c = 0; c < p.block_n; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              red_add_f32x4(wrow + c + 4 * j, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          }
+        }
+      } else if (p.img != nullptr) {
         // 3-channel image epilogue (N padded to 16): fp32 NCHW planes, optional sigmoid / accumulate
         uint32_t r[32];
         tmem_ld_32x32(taddr, r);   // columns >= 16 are never written by the MMA and are ignored
@@ -329,6 +347,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// split-K finish: fp32 workspace -> bf16 output (8 elements per thread)
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ ws, bf16* __restrict__ out, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(ws + i * 8);
+    const float4 b = *reinterpret_cast<const float4*>(ws + i * 8 + 4);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(f);
   }
 }
 
@@ -589,6 +618,10 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 // ------------------------------------------------------------------------------------------------
 // host side (tensor-map helpers live in tma_host.cuh)
 // ------------------------------------------------------------------------------------------------
+// split-K workspace registered by the host (dg_conv_set_splitk_workspace); split-K is off without it
+float* g_splitk_ws = nullptr;
+size_t g_splitk_ws_bytes = 0;
+
 struct ConvGemmExtras {
   const void* mask = nullptr;
   float mask_slope = 0.f;
@@ -630,6 +663,13 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     bn = cands[i];
     if ((long long)m_tiles * (N / bn) >= num_sms()) break;
   }
+  // SM-starved big GEMMs (few M tiles, long K): prefer the widest N tile (best bytes/FLOP) and fill the machine with
+  // split-K instead of shrinking the tile
+  const double gflop_all = 2.0 * B * Hs * Ws * (double)Cs * Cb * 16 * 1e-9;
+  const int k_iters_all = (mode == 0 ? 16 : 4) * ((mode == 0 ? Cb : Cs) / 64);
+  if (!img_mode && !ex.mask && g_splitk_ws && gflop_all > 16.0 && k_iters_all >= 64 && N % 256 == 0 &&
+      (long long)m_tiles * (N / 256) * 2 <= num_sms())
+    bn = 256;
   p.block_n = bn;
   p.n_tiles = N / bn;
   p.num_tiles = m_tiles * p.n_tiles;
@@ -642,10 +682,32 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   p.img_sigmoid = ex.img_sigmoid;
   p.img_accumulate = ex.img_accumulate;
   p.stat_part = ex.stat_part;
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  // split-K for big GEMMs that would leave most SMs idle (M = B*Hs*Ws small, K = taps*Ck large): partial tiles are
+  // accumulated in an fp32 workspace and converted afterwards; such launches cannot fuse the BatchNorm statistics
+  p.splits = 1;
+  p.kps = p.k_iters;
+  p.ws = nullptr;
+  const double gflop = 2.0 * B * Hs * Ws * (double)Cs * Cb * 16 * 1e-9;
+  const size_t ws_need = (size_t)B * p.Ho * p.Wo * N * sizeof(float);
+  if (!img_mode && !ex.mask && g_splitk_ws && ws_need <= g_splitk_ws_bytes && gflop > 16.0 &&
+      p.num_tiles * 2 <= num_sms() && p.k_iters >= 64) {
+    int splits = num_sms() / p.num_tiles;
+    if (splits > p.k_iters / 32) splits = p.k_iters / 32;
+    if (splits > 1) {
+      p.kps = dg_ceil_div(p.k_iters, splits);
+      p.splits = dg_ceil_div(p.k_iters, p.kps);
+      p.ws = g_splitk_ws;
+    }
+  }
+  const int work = p.num_tiles * p.splits;
+  const int grid = work < num_sms() ? work : num_sms();
   if (ex.grid_out) {
-    *ex.grid_out = grid;
+    *ex.grid_out = p.ws ? 0 : grid;   // 0: statistics cannot be fused for this shape (split-K)
     return DG_OK;
+  }
+  if (p.ws) {
+    DG_CHECK_ARG(ex.stat_part == nullptr, "conv gemm: fused statistics requested for a split-K shape");
+    cudaMemsetAsync(p.ws, 0, ws_need, stream);
   }
   const int stage_bytes = kATileBytes + bn * 128;
   int stages = (200 * 1024) / stage_bytes;
@@ -677,6 +739,13 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   }
   conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
   DG_CHECK_LAUNCH("conv_gemm_kernel");
+  if (p.ws) {
+    const long long n8 = (long long)(ws_need / sizeof(float)) / 8;
+    long long blocks = (n8 + 255) / 256;
+    if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+    splitk_finish_kernel<<<(int)blocks, 256, 0, stream>>>(p.ws, p.out, n8);
+    DG_CHECK_LAUNCH("splitk_finish_kernel");
+  }
   return DG_OK;
 }
 
@@ -717,6 +786,14 @@ int dg_conv4x4s2_fprop(const void* x, const void* wd, void* z, int B, int H, int
 int dg_conv4x4s2_dgrad(const void* dz, const void* wu, void* dx, int B, int Hs, int Ws, int Cs, int Cb,
                        cudaStream_t stream) {
   return launch_conv_gemm(1, dz, wu, dx, B, Hs, Ws, Cs, Cb, stream);
+}
+
+// Register a device workspace for split-K (fp32 [output pixels][N] of the largest split layer; 64 MB covers the
+// 512x512 family).  NULL/0 disables split-K.  The buffer is used by launches on any stream in program order.
+int dg_conv_set_splitk_workspace(void* ws, size_t bytes) {
+  g_splitk_ws = reinterpret_cast<float*>(ws);
+  g_splitk_ws_bytes = ws ? bytes : 0;
+  return DG_OK;
 }
 
 // Forward convolutions with the BatchNorm statistics of their output fused in the epilogue.

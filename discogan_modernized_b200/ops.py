@@ -85,6 +85,32 @@ def device_check():
     check(lib().dg_device_check(), "dg_device_check")
 
 
+_splitk_ws = {}
+_splitk_enabled = set()
+
+
+def enable_splitk(device, nbytes=64 << 20):
+    """Allow split-K for the SM-starved deep layers on this device (the trainer turns it on).  Each lane gets its own
+    fp32 workspace; the pointer of the current lane is handed to the C library right before every GEMM launch."""
+    _splitk_enabled.add((torch.device(device), nbytes))
+
+
+def _splitk_select(device):
+    """Point the C library at the current lane's split-K workspace (or disable split-K)."""
+    for dev, nbytes in _splitk_enabled:
+        if dev == device:
+            key = (dev, _lane)
+            buf = _splitk_ws.get(key)
+            if buf is None:
+                if torch.cuda.is_current_stream_capturing():
+                    raise KernelError("split-K workspace would be allocated during CUDA-graph capture; run one eager step first")
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                _splitk_ws[key] = buf
+            lib().dg_conv_set_splitk_workspace(buf.data_ptr(), nbytes)
+            return
+    lib().dg_conv_set_splitk_workspace(None, 0)
+
+
 # ---- weights / layout ---------------------------------------------------------------------
 def pack_weights(w, want_wd=True, want_wu=True, out=None):
     """fp32 [Cs,Cb,4,4] -> (bf16 Wd [Cs,16,Cb], bf16 Wu [Cb,16,Cs]); `out=(wd, wu)` re-packs in place."""
@@ -133,6 +159,7 @@ def conv_down(big, wd):
     B, H, W, Cb = big.shape
     Cs = wd.shape[0]
     out = torch.empty(B, H // 2, W // 2, Cs, dtype=BF16, device=big.device)
+    _splitk_select(big.device)
     fn = lib().dg_conv4x4s2_fprop if _conv_impl == "tc" else lib().dg_simt_conv4x4s2_fprop
     check(fn(_ptr(big, BF16, "big"), _ptr(wd, BF16, "wd"), _ptr(out), B, H, W, Cb, Cs, _stream()), "dg_conv4x4s2_fprop")
     return out
@@ -144,6 +171,7 @@ def conv_up(small, wu, mask=None, slope=0.2):
     B, Hs, Ws, Cs = small.shape
     Cb = wu.shape[0]
     out = torch.empty(B, 2 * Hs, 2 * Ws, Cb, dtype=BF16, device=small.device)
+    _splitk_select(small.device)
     if _conv_impl == "tc" and mask is not None:
         check(lib().dg_conv4x4s2_dgrad_masked(_ptr(small, BF16, "small"), _ptr(wu, BF16, "wu"), _ptr(out),
                                               _ptr(mask, BF16, "mask"), slope, B, Hs, Ws, Cs, Cb, _stream()),
@@ -161,9 +189,10 @@ def conv_down_stats(big, wd):
     """conv_down that also returns per-CTA partial BatchNorm sums of its output: (out, part fp32 [2, rows, Cs])."""
     B, H, W, Cb = big.shape
     Cs = wd.shape[0]
+    _splitk_select(big.device)
     rows = lib().dg_conv_stats_rows(0, B, H // 2, W // 2, Cs, Cb)
-    if rows <= 0:
-        raise KernelError(f"conv_down_stats: unsupported shape {tuple(big.shape)} x Cs={Cs}")
+    if rows <= 0:        # split-K shape: no fused statistics
+        return conv_down(big, wd), None
     out = torch.empty(B, H // 2, W // 2, Cs, dtype=BF16, device=big.device)
     part = torch.empty(2, rows, Cs, dtype=F32, device=big.device)
     check(lib().dg_conv4x4s2_fprop_stats(_ptr(big, BF16, "big"), _ptr(wd, BF16, "wd"), _ptr(out), _ptr(part), B, H, W, Cb,
@@ -175,9 +204,10 @@ def conv_up_stats(small, wu):
     """conv_up (ConvTranspose2d forward) with fused partial BatchNorm sums: (out, part fp32 [2, rows, Cb])."""
     B, Hs, Ws, Cs = small.shape
     Cb = wu.shape[0]
+    _splitk_select(small.device)
     rows = lib().dg_conv_stats_rows(1, B, Hs, Ws, Cs, Cb)
-    if rows <= 0:
-        raise KernelError(f"conv_up_stats: unsupported shape {tuple(small.shape)} x Cb={Cb}")
+    if rows <= 0:        # split-K shape: no fused statistics
+        return conv_up(small, wu), None
     out = torch.empty(B, 2 * Hs, 2 * Ws, Cb, dtype=BF16, device=small.device)
     part = torch.empty(2, rows, Cb, dtype=F32, device=small.device)
     check(lib().dg_convT4x4s2_fprop_stats(_ptr(small, BF16, "small"), _ptr(wu, BF16, "wu"), _ptr(out), _ptr(part), B, Hs,

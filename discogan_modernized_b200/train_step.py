@@ -167,6 +167,8 @@ class DiscoGANTrainer:
         if self.device.index is not None:
             torch.cuda.set_device(self.device)
         ops.device_check()
+        if os.environ.get("DISCOGAN_B200_SPLITK", "1") != "0":
+            ops.enable_splitk(self.device)
         self.image_size = image_size
         self.model_arch = model_arch
         loss_coefficients(model_arch, 0.5)  # validates

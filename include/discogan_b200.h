@@ -50,9 +50,12 @@ int dg_conv4x4s2_fprop(const void* x_big, const void* wd, void* z_small, int B, 
 /* its data gradient (cuDNN bwd-data); also nn.ConvTranspose2d(ci,co,4,2,1) forward, model.py:118-138 */
 int dg_conv4x4s2_dgrad(const void* dz_small, const void* wu, void* dx_big, int B, int Hs, int Ws, int Cs, int Cb,
                        dg_stream_t stream);
+/* device workspace for split-K of the small-M / large-K layers (fp32 [output pixels][N]); NULL disables split-K */
+int dg_conv_set_splitk_workspace(void* ws, size_t bytes);
 /* forward convolutions with the BatchNorm statistics of the output fused in the epilogue: stat_part = float[2*rows*N]
  * (rows = dg_conv_stats_rows, N = output channels) holds per-CTA partial sums / sums of squares of the fp32
- * accumulators; finish with dg_bn_stats_finalize.  mode 0 = Conv2d fprop, 1 = ConvTranspose2d fprop. */
+ * accumulators; finish with dg_bn_stats_finalize.  mode 0 = Conv2d fprop, 1 = ConvTranspose2d fprop.
+ * dg_conv_stats_rows returns 0 for shapes that run split-K (use dg_conv4x4s2_fprop + dg_bn_stats there). */
 int dg_conv_stats_rows(int mode, int B, int Hs, int Ws, int Cs, int Cb);
 int dg_conv4x4s2_fprop_stats(const void* x_big, const void* wd, void* z_small, float* stat_part, int B, int H, int W,
                              int Cb, int Cs, dg_stream_t stream);

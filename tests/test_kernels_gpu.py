@@ -404,3 +404,30 @@ def test_conv_fused_bn_stats(B, H, Cb, Cs):
     stu = ops.bn_stats_finalize(partu, Pu, gb, bb)
     refu = ops.bn_stats(zu.view(Pu, Cb), gb, bb)
     assert torch.allclose(stu[0], refu[0], atol=3e-3, rtol=1e-2) and torch.allclose(stu[1], refu[1], rtol=1e-2)
+
+
+def test_conv_splitk_deep_layer():
+    """The SM-starved deep shapes (M = B*16 pixels, K = 16*2048) run split-K: fp32 partial tiles reduced in a
+    workspace, then converted -- same numbers as the direct kernel."""
+    ops = ops_mod()
+    B, H, Cb, Cs = 32, 8, 2048, 2048
+    x = rnd(B, Cb, H, H, seed=1).to(BF16)
+    w = (rnd(Cs, Cb, 4, 4, seed=2) / (4 * Cb ** 0.5)).to(BF16).float()
+    wd, wu = ops.pack_weights(w)
+    xn = to_nhwc_bf16(x.float())
+    ref = F.conv2d(x.float(), w, stride=2, padding=1)
+    plain = ops.conv_down(xn, wd)                      # split-K is off until enabled
+    assert rel_l2(to_nchw_f32(plain), ref) < 4e-3
+    ops.enable_splitk(xn.device)
+    try:
+        out = ops.conv_down(xn, wd)
+        assert rel_l2(to_nchw_f32(out), ref) < 4e-3
+        z, part = ops.conv_down_stats(xn, wd)          # no fused statistics for a split-K shape
+        assert part is None and torch.equal(z, out)
+        s = rnd(B, Cs, H // 2, H // 2, seed=3).to(BF16)
+        refu = F.conv_transpose2d(s.float(), w, stride=2, padding=1)
+        up = ops.conv_up(to_nhwc_bf16(s.float()), wu)
+        assert rel_l2(to_nchw_f32(up), refu) < 4e-3
+    finally:
+        ops._splitk_enabled.clear()
+        ops._splitk_select(xn.device)
