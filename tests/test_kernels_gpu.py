@@ -423,7 +423,7 @@ def test_conv_splitk_deep_layer():
         out = ops.conv_down(xn, wd)
         assert rel_l2(to_nchw_f32(out), ref) < 4e-3
         z, part = ops.conv_down_stats(xn, wd)          # no fused statistics for a split-K shape
-        assert part is None and torch.equal(z, out)
+        assert part is None and rel_l2(z, out) < 2e-3   # (atomic accumulation order: not bit-reproducible)
         s = rnd(B, Cs, H // 2, H // 2, seed=3).to(BF16)
         refu = F.conv_transpose2d(s.float(), w, stride=2, padding=1)
         up = ops.conv_up(to_nhwc_bf16(s.float()), wu)
