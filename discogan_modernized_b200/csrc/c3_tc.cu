@@ -29,6 +29,8 @@ constexpr uint32_t kSw32 = 6;  // UMMA layout type SWIZZLE_32B
 __global__ void __launch_bounds__(256)
 img_pad_nhwc4_kernel(const float* __restrict__ img, const float* __restrict__ img2, const float* __restrict__ yimg,
                      bf16* __restrict__ out, int B, int S) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int Sp = S + 2;
   const long long total = (long long)B * Sp * Sp;
   const size_t plane = (size_t)S * S;
@@ -60,6 +62,8 @@ img_pad_nhwc4_kernel(const float* __restrict__ img, const float* __restrict__ im
 
 // w fp32 [64][3][4][4] -> wc bf16 [64][kh*16 + kw*4 + c] (c = 3 zero) and wu3 bf16 [16][tap][64] (rows >= 3 zero)
 __global__ void c3_pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wc, bf16* __restrict__ wu3) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (wc && i < 64 * 64) {
     const int c64 = i >> 6, k = i & 63;
@@ -122,6 +126,10 @@ c3_down_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // programmatic dependent launch: dependents may be scheduled once every CTA of this grid holds its TMEM columns;
+  // nothing above touches global memory, everything below runs after the predecessor grid has completed
+  griddep_launch_dependents();
+  griddep_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -268,6 +276,10 @@ c3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // programmatic dependent launch: dependents may be scheduled once every CTA of this grid holds its TMEM columns;
+  // nothing above touches global memory, everything below runs after the predecessor grid has completed
+  griddep_launch_dependents();
+  griddep_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -345,6 +357,8 @@ c3_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constan
 
 // dw[c64][c][kh][kw] = beta*dw + sum_split ws[split][c64][kh*16 + kw*4 + c]
 __global__ void c3_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float beta, int splits) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 48) return;
   const int c64 = i / 48, r = i % 48, c = r >> 4, kh = (r >> 2) & 3, kw = r & 3;
@@ -369,7 +383,7 @@ extern "C" {
 
 int dg_c3_pack_weights(const float* w, void* wc, void* wu3, cudaStream_t stream) {
   DG_CHECK_ARG(w && (wc || wu3), "c3_pack_weights: bad args");
-  c3_pack_weights_kernel<<<64, 256, 0, stream>>>(w, (bf16*)wc, (bf16*)wu3);
+  dg_launch(c3_pack_weights_kernel, dg_cfg(64, 256, 0, stream), w, (bf16*)wc, (bf16*)wu3);
   DG_CHECK_LAUNCH("c3_pack_weights");
   return DG_OK;
 }
@@ -382,7 +396,7 @@ int dg_img_pad_nhwc4(const float* img, const float* img2, const float* yimg, voi
   const long long total = (long long)B * (S + 2) * (S + 2);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  img_pad_nhwc4_kernel<<<(int)blocks, 256, 0, stream>>>(img, img2, yimg, (bf16*)out, B, S);
+  dg_launch(img_pad_nhwc4_kernel, dg_cfg((int)blocks, 256, 0, stream), img, img2, yimg, (bf16*)out, B, S);
   DG_CHECK_LAUNCH("img_pad_nhwc4");
   return DG_OK;
 }
@@ -419,7 +433,7 @@ int dg_c3_down_tc(const void* xp, const void* wc, void* y, int B, int S, int act
     attr_set = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  c3_down_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmP, tmW, p);
+  dg_launch(c3_down_tc_kernel, dg_cfg(grid, kThreads, smem_bytes, stream), tmP, tmW, p);
   DG_CHECK_LAUNCH("c3_down_tc_kernel");
   return DG_OK;
 }
@@ -465,9 +479,9 @@ int dg_c3_wgrad_tc(const void* v64, const void* xp, float* dw, float beta, int B
     }
     attr_set = true;
   }
-  c3_wgrad_tc_kernel<<<p.splits, kThreads, smem_bytes, stream>>>(tmV, tmP, p);
+  dg_launch(c3_wgrad_tc_kernel, dg_cfg(p.splits, kThreads, smem_bytes, stream), tmV, tmP, p);
   DG_CHECK_LAUNCH("c3_wgrad_tc_kernel");
-  c3_wgrad_reduce_kernel<<<12, 256, 0, stream>>>(p.ws, dw, beta, p.splits);
+  dg_launch(c3_wgrad_reduce_kernel, dg_cfg(12, 256, 0, stream), p.ws, dw, beta, p.splits);
   DG_CHECK_LAUNCH("c3_wgrad_reduce_kernel");
   return DG_OK;
 }

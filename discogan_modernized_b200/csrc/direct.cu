@@ -23,6 +23,8 @@ template <bool SIGGRAD>
 __global__ void __launch_bounds__(256)
 c3_down_kernel(const float* __restrict__ img, const float* __restrict__ yimg, const float* __restrict__ w,
                bf16* __restrict__ out, int B, int S, int act, float slope) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float ws[48][kC1];  // [k = c*16 + kh*4 + kw][co]
   for (int i = threadIdx.x; i < 48 * kC1; i += blockDim.x) {
     const int co = i / 48, k = i % 48;
@@ -88,6 +90,8 @@ template <bool MASK>
 __global__ void __launch_bounds__(256)
 c3_up_kernel(const bf16* __restrict__ act64, const bf16* __restrict__ y64, const float* __restrict__ w,
              float* __restrict__ img, int B, int S, int sigmoid, float slope, int accumulate) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float ws[16][kC1][3];  // [kh*4+kw][c64][c3]
   for (int i = threadIdx.x; i < 48 * kC1; i += blockDim.x) {
     const int c64 = i / 48, r = i % 48, c3 = r / 16, t = r % 16;
@@ -162,6 +166,8 @@ __global__ void __launch_bounds__(256)
 c3_wgrad_kernel(const bf16* __restrict__ v64, const bf16* __restrict__ y64, const float* __restrict__ img,
                 const float* __restrict__ yimg, float* __restrict__ dw, int B, int S, float slope,
                 int pix_per_block) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float sv[32][kC1];
   __shared__ float sp[32][48];
   const int So = S >> 1;
@@ -241,6 +247,8 @@ template <typename TS>
 __global__ void __launch_bounds__(256)
 fc_down_kernel(const bf16* __restrict__ big, const bf16* __restrict__ wd, TS* __restrict__ small, int B, int Ns,
                int K) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int n0 = blockIdx.x * 4, b0 = blockIdx.y * 8;
   float acc[4][8];
 #pragma unroll
@@ -292,6 +300,8 @@ fc_down_kernel(const bf16* __restrict__ big, const bf16* __restrict__ wd, TS* __
 template <typename TS>
 __global__ void __launch_bounds__(128)
 fc_up_kernel(const TS* __restrict__ small, const bf16* __restrict__ wd, bf16* __restrict__ big, int B, int Ns, int K) {
+  griddep_launch_dependents();
+  griddep_wait();
   extern __shared__ float ssm[];  // [4][Ns]
   const int b0 = blockIdx.y * 4;
   for (int i = threadIdx.x; i < 4 * Ns; i += blockDim.x) {
@@ -328,6 +338,8 @@ template <typename TS>
 __global__ void __launch_bounds__(128)
 fc_wgrad_kernel(const TS* __restrict__ small, const bf16* __restrict__ big, float* __restrict__ dw, float beta, int B,
                 int Ns, int C) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int n = blockIdx.y;
   const int cv = C >> 3;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,6 +371,8 @@ fc_wgrad_kernel(const TS* __restrict__ small, const bf16* __restrict__ big, floa
 // ------------------------------------------------------------------------------------------------
 __global__ void simt_down_kernel(const bf16* __restrict__ big, const bf16* __restrict__ wd, bf16* __restrict__ small,
                                  int B, int Hs, int Ws, int Cs, int Cb) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * Hs * Ws * Cs;
   if (idx >= total) return;
@@ -385,6 +399,8 @@ __global__ void simt_down_kernel(const bf16* __restrict__ big, const bf16* __res
 }
 __global__ void simt_up_kernel(const bf16* __restrict__ small, const bf16* __restrict__ wu, bf16* __restrict__ big,
                                int B, int Hs, int Ws, int Cs, int Cb) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int H = 2 * Hs, W = 2 * Ws;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * H * W * Cb;
@@ -415,6 +431,8 @@ __global__ void simt_up_kernel(const bf16* __restrict__ small, const bf16* __res
 }
 __global__ void simt_wgrad_kernel(const bf16* __restrict__ small, const bf16* __restrict__ big, float* __restrict__ dw,
                                   float beta, int B, int Hs, int Ws, int Cs, int Cb) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)Cs * Cb * 16;
   if (idx >= total) return;
@@ -445,7 +463,7 @@ extern "C" {
 int dg_conv_c3_in_fwd(const float* x, const float* w, void* y, int B, int S, float slope, cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && S >= 4 && S % 2 == 0 && x && w && y, "conv_c3_in_fwd: bad args");
   const long long threads = (long long)B * (S / 2) * (S / 2) * 4;
-  c3_down_kernel<false><<<dg_ceil_div(threads, 256), 256, 0, stream>>>(x, nullptr, w, (bf16*)y, B, S, DG_ACT_LRELU,
+  dg_launch(c3_down_kernel<false>, dg_cfg(dg_ceil_div(threads, 256), 256, 0, stream), x, nullptr, w, (bf16*)y, B, S, DG_ACT_LRELU,
                                                                        slope);
   DG_CHECK_LAUNCH("conv_c3_in_fwd");
   return DG_OK;
@@ -457,7 +475,7 @@ int dg_conv_c3_in_bwd(const float* x, const float* w, const void* y, const void*
   DG_CHECK_ARG(B > 0 && S >= 4 && S % 2 == 0 && w && y && dy, "conv_c3_in_bwd: bad args");
   if (dx) {
     const long long threads = (long long)B * S * S;
-    c3_up_kernel<true><<<dg_ceil_div(threads, 256), 256, 0, stream>>>((const bf16*)dy, (const bf16*)y, w, dx, B, S, 0,
+    dg_launch(c3_up_kernel<true>, dg_cfg(dg_ceil_div(threads, 256), 256, 0, stream), (const bf16*)dy, (const bf16*)y, w, dx, B, S, 0,
                                                                       slope, dx_accumulate);
     DG_CHECK_LAUNCH("conv_c3_in_dgrad");
   }
@@ -466,7 +484,7 @@ int dg_conv_c3_in_bwd(const float* x, const float* w, const void* y, const void*
     const long long npix = (long long)B * (S / 2) * (S / 2);
     int ppb = (int)((npix + 591) / 592);
     ppb = (ppb + 31) / 32 * 32;
-    c3_wgrad_kernel<true, false><<<dg_ceil_div(npix, ppb), 256, 0, stream>>>((const bf16*)dy, (const bf16*)y, x,
+    dg_launch(c3_wgrad_kernel<true, false>, dg_cfg(dg_ceil_div(npix, ppb), 256, 0, stream), (const bf16*)dy, (const bf16*)y, x,
                                                                              nullptr, dw, B, S, slope, ppb);
     DG_CHECK_LAUNCH("conv_c3_in_wgrad");
   }
@@ -476,7 +494,7 @@ int dg_conv_c3_in_bwd(const float* x, const float* w, const void* y, const void*
 int dg_convT_c3_out_fwd(const void* x, const float* w, float* y, int B, int S, cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && S >= 4 && S % 2 == 0 && x && w && y, "convT_c3_out_fwd: bad args");
   const long long threads = (long long)B * S * S;
-  c3_up_kernel<false><<<dg_ceil_div(threads, 256), 256, 0, stream>>>((const bf16*)x, nullptr, w, y, B, S, 1, 0.f, 0);
+  dg_launch(c3_up_kernel<false>, dg_cfg(dg_ceil_div(threads, 256), 256, 0, stream), (const bf16*)x, nullptr, w, y, B, S, 1, 0.f, 0);
   DG_CHECK_LAUNCH("convT_c3_out_fwd");
   return DG_OK;
 }
@@ -487,7 +505,7 @@ int dg_convT_c3_out_bwd(const void* x, const float* w, const float* y, const flo
   DG_CHECK_ARG(B > 0 && S >= 4 && S % 2 == 0 && w && y && dy, "convT_c3_out_bwd: bad args");
   if (dx) {
     const long long threads = (long long)B * (S / 2) * (S / 2) * 4;
-    c3_down_kernel<true><<<dg_ceil_div(threads, 256), 256, 0, stream>>>(dy, y, w, (bf16*)dx, B, S, DG_ACT_NONE, 0.f);
+    dg_launch(c3_down_kernel<true>, dg_cfg(dg_ceil_div(threads, 256), 256, 0, stream), dy, y, w, (bf16*)dx, B, S, DG_ACT_NONE, 0.f);
     DG_CHECK_LAUNCH("convT_c3_out_dgrad");
   }
   if (dw) {
@@ -495,7 +513,7 @@ int dg_convT_c3_out_bwd(const void* x, const float* w, const float* y, const flo
     const long long npix = (long long)B * (S / 2) * (S / 2);
     int ppb = (int)((npix + 591) / 592);
     ppb = (ppb + 31) / 32 * 32;
-    c3_wgrad_kernel<false, true><<<dg_ceil_div(npix, ppb), 256, 0, stream>>>((const bf16*)x, nullptr, dy, y, dw, B, S,
+    dg_launch(c3_wgrad_kernel<false, true>, dg_cfg(dg_ceil_div(npix, ppb), 256, 0, stream), (const bf16*)x, nullptr, dy, y, dw, B, S,
                                                                              0.f, ppb);
     DG_CHECK_LAUNCH("convT_c3_out_wgrad");
   }
@@ -507,9 +525,9 @@ int dg_fc_down(const void* big, const void* wd, void* small, int small_f32, int 
   DG_CHECK_ARG(B > 0 && Ns > 0 && K > 0 && K % 8 == 0, "fc_down: bad dims");
   dim3 grid(dg_ceil_div(Ns, 4), dg_ceil_div(B, 8));
   if (small_f32)
-    fc_down_kernel<float><<<grid, 256, 0, stream>>>((const bf16*)big, (const bf16*)wd, (float*)small, B, Ns, K);
+    dg_launch(fc_down_kernel<float>, dg_cfg(grid, 256, 0, stream), (const bf16*)big, (const bf16*)wd, (float*)small, B, Ns, K);
   else
-    fc_down_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)big, (const bf16*)wd, (bf16*)small, B, Ns, K);
+    dg_launch(fc_down_kernel<bf16>, dg_cfg(grid, 256, 0, stream), (const bf16*)big, (const bf16*)wd, (bf16*)small, B, Ns, K);
   DG_CHECK_LAUNCH("fc_down");
   return DG_OK;
 }
@@ -518,9 +536,9 @@ int dg_fc_up(const void* small, int small_f32, const void* wd, void* big, int B,
   dim3 grid(dg_ceil_div(K / 8, 128), dg_ceil_div(B, 4));
   const size_t smem = (size_t)4 * Ns * sizeof(float);
   if (small_f32)
-    fc_up_kernel<float><<<grid, 128, smem, stream>>>((const float*)small, (const bf16*)wd, (bf16*)big, B, Ns, K);
+    dg_launch(fc_up_kernel<float>, dg_cfg(grid, 128, smem, stream), (const float*)small, (const bf16*)wd, (bf16*)big, B, Ns, K);
   else
-    fc_up_kernel<bf16><<<grid, 128, smem, stream>>>((const bf16*)small, (const bf16*)wd, (bf16*)big, B, Ns, K);
+    dg_launch(fc_up_kernel<bf16>, dg_cfg(grid, 128, smem, stream), (const bf16*)small, (const bf16*)wd, (bf16*)big, B, Ns, K);
   DG_CHECK_LAUNCH("fc_up");
   return DG_OK;
 }
@@ -529,9 +547,9 @@ int dg_fc_wgrad(const void* small, int small_f32, const void* big, float* dw, fl
   DG_CHECK_ARG(B > 0 && Ns > 0 && C > 0 && C % 8 == 0 && Ns <= 65535, "fc_wgrad: bad dims");
   dim3 grid(dg_ceil_div(2 * C, 128), Ns);
   if (small_f32)
-    fc_wgrad_kernel<float><<<grid, 128, 0, stream>>>((const float*)small, (const bf16*)big, dw, beta, B, Ns, C);
+    dg_launch(fc_wgrad_kernel<float>, dg_cfg(grid, 128, 0, stream), (const float*)small, (const bf16*)big, dw, beta, B, Ns, C);
   else
-    fc_wgrad_kernel<bf16><<<grid, 128, 0, stream>>>((const bf16*)small, (const bf16*)big, dw, beta, B, Ns, C);
+    dg_launch(fc_wgrad_kernel<bf16>, dg_cfg(grid, 128, 0, stream), (const bf16*)small, (const bf16*)big, dw, beta, B, Ns, C);
   DG_CHECK_LAUNCH("fc_wgrad");
   return DG_OK;
 }
@@ -540,7 +558,7 @@ int dg_fc_wgrad(const void* small, int small_f32, const void* big, float* dw, fl
 int dg_simt_conv4x4s2_fprop(const void* x, const void* wd, void* z, int B, int H, int W, int Cb, int Cs,
                             cudaStream_t stream) {
   const long long total = (long long)B * (H / 2) * (W / 2) * Cs;
-  simt_down_kernel<<<dg_ceil_div(total, 256), 256, 0, stream>>>((const bf16*)x, (const bf16*)wd, (bf16*)z, B, H / 2,
+  dg_launch(simt_down_kernel, dg_cfg(dg_ceil_div(total, 256), 256, 0, stream), (const bf16*)x, (const bf16*)wd, (bf16*)z, B, H / 2,
                                                                W / 2, Cs, Cb);
   DG_CHECK_LAUNCH("simt_down");
   return DG_OK;
@@ -548,7 +566,7 @@ int dg_simt_conv4x4s2_fprop(const void* x, const void* wd, void* z, int B, int H
 int dg_simt_conv4x4s2_dgrad(const void* dz, const void* wu, void* dx, int B, int Hs, int Ws, int Cs, int Cb,
                             cudaStream_t stream) {
   const long long total = (long long)B * Hs * Ws * 4 * Cb;
-  simt_up_kernel<<<dg_ceil_div(total, 256), 256, 0, stream>>>((const bf16*)dz, (const bf16*)wu, (bf16*)dx, B, Hs, Ws,
+  dg_launch(simt_up_kernel, dg_cfg(dg_ceil_div(total, 256), 256, 0, stream), (const bf16*)dz, (const bf16*)wu, (bf16*)dx, B, Hs, Ws,
                                                              Cs, Cb);
   DG_CHECK_LAUNCH("simt_up");
   return DG_OK;
@@ -556,7 +574,7 @@ int dg_simt_conv4x4s2_dgrad(const void* dz, const void* wu, void* dx, int B, int
 int dg_simt_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
                             int Cb, cudaStream_t stream) {
   const long long total = (long long)Cs * Cb * 16;
-  simt_wgrad_kernel<<<dg_ceil_div(total, 256), 256, 0, stream>>>((const bf16*)small, (const bf16*)big, dw, beta, B, Hs,
+  dg_launch(simt_wgrad_kernel, dg_cfg(dg_ceil_div(total, 256), 256, 0, stream), (const bf16*)small, (const bf16*)big, dw, beta, B, Hs,
                                                                 Ws, Cs, Cb);
   DG_CHECK_LAUNCH("simt_wgrad");
   return DG_OK;

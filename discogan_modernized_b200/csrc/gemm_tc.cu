@@ -131,6 +131,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // programmatic dependent launch: dependents may be scheduled once every CTA of this grid holds its TMEM columns;
+  // nothing above touches global memory, everything below runs after the predecessor grid has completed
+  griddep_launch_dependents();
+  griddep_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -353,6 +357,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // split-K finish: fp32 workspace -> bf16 output (8 elements per thread)
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const float* __restrict__ ws, bf16* __restrict__ out, long long n8) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = *reinterpret_cast<const float4*>(ws + i * 8);
     const float4 b = *reinterpret_cast<const float4*>(ws + i * 8 + 4);
@@ -379,6 +385,8 @@ struct WgradParams {
   float* dw;  // direct mode (splits == 1): the epilogue writes dw = beta*dw + acc in PyTorch layout itself
   float beta;
   int direct;
+  int cluster;  // 1: launched as clusters of 2 CTAs = two m-tiles of the same (n-tile, tap half, split); the 8 tap boxes
+                // of `big` are identical for both, so each CTA fetches 4 of them and TMA-multicasts them to the pair
   int debug;  // timing experiments only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
   int share;  // 0: one TMA box per tap.  1/2: taps that differ by a one-pixel shift inside the same parity plane share a
               // 33-pixel box and are addressed with a 128-byte row offset (1: descriptor base_offset = row phase, 2: 0)
@@ -400,11 +408,24 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  int w = blockIdx.x;
-  const int half = w & 1;
-  w >>= 1;
-  const int nt = w % p.n_tiles;
-  const int mt = w / p.n_tiles;
+  int half, nt, mt;
+  uint32_t crank = 0;
+  if (p.cluster) {
+    crank = cluster_ctarank();
+    int v = blockIdx.x >> 1;
+    const int mp = v % (p.m_tiles >> 1);
+    v /= (p.m_tiles >> 1);
+    half = v & 1;
+    nt = v >> 1;
+    mt = 2 * mp + (int)crank;
+  } else {
+    int w = blockIdx.x;
+    half = w & 1;
+    w >>= 1;
+    nt = w % p.n_tiles;
+    mt = w / p.n_tiles;
+  }
+  const uint16_t cmask = p.cluster ? (uint16_t)3 : (uint16_t)1;
   const int split = blockIdx.y;
   const int chunk_begin = split * p.chunks_per_split;
   const int chunk_end = min(p.total_chunks, chunk_begin + p.chunks_per_split);
@@ -414,7 +435,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
     tma_prefetch_desc(&tmBig);
     for (int s = 0; s < kWgStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], p.cluster ? 2 : 1);   // a stage is free once BOTH CTAs of the pair have consumed it
     }
     mbar_init(tfull_bar, 1);
     fence_mbar_init();
@@ -423,6 +444,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (p.cluster) cluster_sync_all();   // the peer's barriers are initialised before any multicast traffic
+  // programmatic dependent launch: dependents may be scheduled once every CTA of this grid holds its TMEM columns;
+  // nothing above touches global memory, everything below runs after the predecessor grid has completed
+  griddep_launch_dependents();
+  griddep_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -466,7 +492,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
           const int kh = tap >> 2, kw = tap & 3;
           const int dh = ((kh + 1) >> 1) - 1, ph = (kh + 1) & 1;
           const int dw = ((kw + 1) >> 1) - 1, pw = (kw + 1) & 1;
-          tma_load_5d(sb + t * kWgBoxBytes, &tmBig, &full_bar[stage], pw * p.Cb + nt * 64, w0 + dw, ph, h0 + dh, b0);
+          if (!p.cluster)
+            tma_load_5d(sb + t * kWgBoxBytes, &tmBig, &full_bar[stage], pw * p.Cb + nt * 64, w0 + dw, ph, h0 + dh, b0);
+          else if ((uint32_t)(t & 1) == crank)
+            tma_load_5d_mc(sb + t * kWgBoxBytes, &tmBig, &full_bar[stage], pw * p.Cb + nt * 64, w0 + dw, ph, h0 + dh,
+                           b0, cmask);
         }
         if (++stage == kWgStages) {
           stage = 0;
@@ -512,7 +542,10 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
             }
           }
         }
-        umma_commit(&empty_bar[stage]);
+        if (p.cluster)
+          umma_commit_mc(&empty_bar[stage], cmask);
+        else
+          umma_commit(&empty_bar[stage]);
         if (++stage == kWgStages) {
           stage = 0;
           phase ^= 1u;
@@ -574,6 +607,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster) cluster_sync_all();   // neither CTA leaves while the peer can still arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -583,6 +617,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
 // dw[cs][cb][tap] = beta*dw + sum_split ws[...]; one thread per (cs, cb, half) writes 8 consecutive taps.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float beta, int Cs, int Cb,
                                     int m_tiles, int n_tiles, int splits) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)Cs * Cb * 2;
   if (idx >= total) return;
@@ -737,13 +773,13 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     }
     attr_set = true;
   }
-  conv_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
+  dg_launch(conv_gemm_kernel, dg_cfg(grid, kThreads, smem_bytes, stream), tmA, tmB, p);
   DG_CHECK_LAUNCH("conv_gemm_kernel");
   if (p.ws) {
     const long long n8 = (long long)(ws_need / sizeof(float)) / 8;
     long long blocks = (n8 + 255) / 256;
     if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-    splitk_finish_kernel<<<(int)blocks, 256, 0, stream>>>(p.ws, p.out, n8);
+    dg_launch(splitk_finish_kernel, dg_cfg((int)blocks, 256, 0, stream), p.ws, p.out, n8);
     DG_CHECK_LAUNCH("splitk_finish_kernel");
   }
   return DG_OK;
@@ -896,11 +932,17 @@ int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta
   }
   const int smem_bytes = kWgStages * kWgStageBytes + 1024 + 256;
   dim3 grid(p.m_tiles * p.n_tiles * 2, p.splits);
-  wgrad_gemm_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmS, tmBig, tmBig33, p);
+  static int cluster_mode = -1;
+  if (cluster_mode < 0) {
+    const char* e = getenv("DG_WGRAD_CLUSTER");
+    cluster_mode = e ? atoi(e) : 1;
+  }
+  p.cluster = (cluster_mode && !p.share && p.m_tiles % 2 == 0) ? 1 : 0;
+  dg_launch(wgrad_gemm_kernel, dg_cfg(grid, kThreads, smem_bytes, stream, p.cluster ? 2 : 1), tmS, tmBig, tmBig33, p);
   DG_CHECK_LAUNCH("wgrad_gemm_kernel");
   if (p.direct) return DG_OK;
   const long long total = (long long)Cs * Cb * 2;
-  wgrad_reduce_kernel<<<dg_ceil_div(total, 256), 256, 0, stream>>>(p.ws, dw, beta, Cs, Cb, p.m_tiles, p.n_tiles,
+  dg_launch(wgrad_reduce_kernel, dg_cfg(dg_ceil_div(total, 256), 256, 0, stream), p.ws, dw, beta, Cs, Cb, p.m_tiles, p.n_tiles,
                                                                    p.splits);
   DG_CHECK_LAUNCH("wgrad_reduce_kernel");
   return DG_OK;

@@ -28,6 +28,8 @@ namespace {
 // weight packing: W[Cs][Cb][16] fp32 -> Wd[Cs][16][Cb] bf16 (cb fastest), Wu[Cb][16][Cs] bf16 (cs fastest)
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_wd_kernel(const float* __restrict__ w, bf16* __restrict__ wd, int Cs, int Cb) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)Cs * Cb) return;
   const int cb = (int)(idx % Cb);
@@ -43,6 +45,8 @@ __global__ void pack_wd_kernel(const float* __restrict__ w, bf16* __restrict__ w
   for (int t = 0; t < 16; ++t) wd[((size_t)cs * 16 + t) * Cb + cb] = __float2bfloat16(v[t]);
 }
 __global__ void pack_wu_kernel(const float* __restrict__ w, bf16* __restrict__ wu, int Cs, int Cb) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)Cs * Cb) return;
   const int cs = (int)(idx % Cs);
@@ -63,6 +67,8 @@ __global__ void pack_wu_kernel(const float* __restrict__ w, bf16* __restrict__ w
 // the second Cs*Cb write Wu (cs fastest), so both stores stay coalesced.
 __global__ void __launch_bounds__(256)
 pack_multi_kernel(const long long* __restrict__ table, int n, long long total) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ long long tb[64 * 6];
   for (int i = threadIdx.x; i < n * 6; i += blockDim.x) tb[i] = table[i];
   __syncthreads();
@@ -110,6 +116,8 @@ pack_multi_kernel(const long long* __restrict__ table, int n, long long total) {
 // layout: NHWC bf16 [B][HW][C] <-> NCHW fp32 [B][C][HW], 32x32 smem tiles
 // ------------------------------------------------------------------------------------------------
 __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, float* __restrict__ y, int HW, int C) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -124,6 +132,8 @@ __global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ x, float* __restric
   }
 }
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int HW, int C) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -220,6 +230,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 bn_stats_partial_kernel(const bf16* __restrict__ z, long long P, int C, int cw, int rows_iter, int rows_split,
                         float* __restrict__ part_sum, float* __restrict__ part_sq) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
   const int c = (blockIdx.x * cw + tx) * VEC;
   float s1[VEC], s2[VEC];
@@ -261,6 +273,8 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ part_sum, con
                                          float* __restrict__ mean, float* __restrict__ invstd,
                                          float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ running_mean, float* __restrict__ running_var) {
+  griddep_launch_dependents();
+  griddep_wait();
   // block = 32 channels x 8 split lanes; partial rows are summed 8-way in parallel, then combined in smem
   __shared__ double sh_s[8][32], sh_q[8][32];
   const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
@@ -313,6 +327,8 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ part_sum, con
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                       float eps, int C, float* __restrict__ scale, float* __restrict__ shift) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float is = rsqrtf(running_var[c] + eps);
@@ -326,6 +342,8 @@ __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const bf16* __restrict__ z, bf16* __restrict__ y, long long P, int C, int cw, int rows_iter,
                   int rows_split, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                   float slope) {
+  griddep_launch_dependents();
+  griddep_wait();
   // same (channel vectors) x (rows) block shape as the reductions: a thread keeps its channels' coefficients in
   // registers and streams rows -- no per-element index arithmetic
   const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
@@ -387,6 +405,8 @@ bn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2,
                       float coef, long long bcast_rows, const bf16* __restrict__ z, const float* __restrict__ stats,
                       long long P, int C, int cw, int rows_iter, int rows_split, int act, float slope,
                       float* __restrict__ part_g, float* __restrict__ part_gx) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
   const int c = (blockIdx.x * cw + tx) * VEC;
   float s1[VEC], s2[VEC];
@@ -441,6 +461,8 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part_g, const f
                                        long long P, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ invstd, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float beta_acc, float* __restrict__ coefs) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ double sh_s[8][32], sh_q[8][32];
   const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -486,6 +508,8 @@ bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, cons
                  long long bcast_rows, const bf16* __restrict__ z, const float* __restrict__ stats,
                  const float* __restrict__ coefs, bf16* __restrict__ dz, long long P, int C, int cw, int rows_iter,
                  int rows_split, int act, float slope) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
   const int c = (blockIdx.x * cw + tx) * VEC;
   if (c >= C) return;
@@ -555,6 +579,8 @@ __device__ __forceinline__ float block_sum_256(float v) {
 // (nn.BCELoss semantics).  Also writes the probabilities.
 __global__ void gan_bce_fwd_kernel(const float* __restrict__ logit_real, const float* __restrict__ logit_fake, int B,
                                    float* __restrict__ p_real, float* __restrict__ p_fake, float* __restrict__ out) {
+  griddep_launch_dependents();
+  griddep_wait();
   float a = 0.f, b = 0.f, c = 0.f;
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
     const float pr = 1.f / (1.f + expf(-logit_real[i]));
@@ -578,6 +604,8 @@ __global__ void gan_bce_fwd_kernel(const float* __restrict__ logit_real, const f
 __global__ void gan_bce_bwd_kernel(const float* __restrict__ p_real, const float* __restrict__ p_fake, int B,
                                    float g_dis, float g_gen, float* __restrict__ dlogit_real,
                                    float* __restrict__ dlogit_fake) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   const float pr = p_real[i], pf = p_fake[i];
@@ -591,11 +619,15 @@ __global__ void gan_bce_bwd_kernel(const float* __restrict__ p_real, const float
 
 // sigmoid forward/backward on tiny [B] vectors (module API path: prob output of the Discriminator)
 __global__ void sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int n) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = 1.f / (1.f + expf(-x[i]));
 }
 __global__ void sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx,
                                    int n) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dx[i] = dy[i] * y[i] * (1.f - y[i]);
 }
@@ -603,6 +635,8 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ y, const float* __r
 // MSE: partial sums of (a-b)^2 per block, then finalize to mean
 __global__ void __launch_bounds__(256)
 mse_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ part) {
+  griddep_launch_dependents();
+  griddep_wait();
   float s = 0.f;
   const long long n4 = n >> 2;
   const float4* a4 = reinterpret_cast<const float4*>(a);
@@ -622,6 +656,8 @@ mse_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, lon
 }
 __global__ void sum_finalize_kernel(const float* __restrict__ part, int n, double scale, float* __restrict__ out,
                                     int accumulate) {
+  griddep_launch_dependents();
+  griddep_wait();
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += 32) s += (double)part[i];
 #pragma unroll
@@ -635,6 +671,8 @@ __global__ void sum_finalize_kernel(const float* __restrict__ part, int n, doubl
 __global__ void __launch_bounds__(256)
 mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float coef,
                float* __restrict__ da, int accumulate) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = coef * (a[i] - b[i]);
     da[i] = accumulate ? da[i] + v : v;
@@ -646,6 +684,8 @@ mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long lo
 __global__ void __launch_bounds__(256)
 fm_partial_kernel(const bf16* __restrict__ real, const bf16* __restrict__ fake, int B, long long n,
                   float* __restrict__ diff, float* __restrict__ part) {
+  griddep_launch_dependents();
+  griddep_wait();
   float s = 0.f;
   const long long n8 = n >> 3;
   const float invB = 1.f / (float)B;
@@ -698,6 +738,8 @@ fm_partial_kernel(const bf16* __restrict__ real, const bf16* __restrict__ fake, 
 // dfeat[b][i] = coef * diff[i]  (bf16, broadcast over batch)
 __global__ void __launch_bounds__(256)
 fm_bwd_kernel(const float* __restrict__ diff, int B, long long n, float coef, bf16* __restrict__ dfeat) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long n8 = n >> 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float d[8];
@@ -716,6 +758,8 @@ fm_bwd_kernel(const float* __restrict__ diff, int B, long long n, float coef, bf
 // state = {step count, 1 - beta1^step, sqrt(1 - beta2^step), unused}: kept on the device so a captured CUDA graph
 // of the train step advances the bias corrections on every replay.
 __global__ void adam_tick_kernel(float* __restrict__ state, float b1, float b2) {
+  griddep_launch_dependents();
+  griddep_wait();
   const double step = (double)state[0] + 1.0;
   state[0] = (float)step;
   state[1] = (float)(1.0 - pow((double)b1, step));
@@ -726,6 +770,8 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
             long long n4, float lr, float b1, float b2, float eps, float wd, const float* __restrict__ state,
             float grad_scale) {
+  griddep_launch_dependents();
+  griddep_wait();
   const float step_size = lr / state[1];
   const float bc2_sqrt = state[2];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -797,11 +843,11 @@ int dg_pack_weights(const float* w, void* wd, void* wu, int Cs, int Cb, cudaStre
   DG_CHECK_ARG(Cs > 0 && Cb > 0 && w, "pack_weights: bad args");
   const long long n = (long long)Cs * Cb;
   if (wd) {
-    pack_wd_kernel<<<dg_ceil_div(n, 256), 256, 0, stream>>>(w, (bf16*)wd, Cs, Cb);
+    dg_launch(pack_wd_kernel, dg_cfg(dg_ceil_div(n, 256), 256, 0, stream), w, (bf16*)wd, Cs, Cb);
     DG_CHECK_LAUNCH("pack_wd");
   }
   if (wu) {
-    pack_wu_kernel<<<dg_ceil_div(n, 256), 256, 0, stream>>>(w, (bf16*)wu, Cs, Cb);
+    dg_launch(pack_wu_kernel, dg_cfg(dg_ceil_div(n, 256), 256, 0, stream), w, (bf16*)wu, Cs, Cb);
     DG_CHECK_LAUNCH("pack_wu");
   }
   return DG_OK;
@@ -810,7 +856,7 @@ int dg_pack_weights(const float* w, void* wd, void* wu, int Cs, int Cb, cudaStre
 // table: device int64 [n][6] = {w ptr, wd ptr (or 0), wu ptr (or 0), Cs, Cb, running end of 2*Cs*Cb items}; n <= 64
 int dg_pack_weights_multi(const long long* table, int n, long long total_items, cudaStream_t stream) {
   DG_CHECK_ARG(table && n > 0 && n <= 64 && total_items > 0, "pack_weights_multi: bad args");
-  pack_multi_kernel<<<ew_grid(total_items, sms()), 256, 0, stream>>>(table, n, total_items);
+  dg_launch(pack_multi_kernel, dg_cfg(ew_grid(total_items, sms()), 256, 0, stream), table, n, total_items);
   DG_CHECK_LAUNCH("pack_weights_multi");
   return DG_OK;
 }
@@ -818,14 +864,14 @@ int dg_pack_weights_multi(const long long* table, int n, long long total_items, 
 int dg_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && HW > 0 && C > 0 && B <= 65535, "nhwc_to_nchw: bad dims");
   dim3 grid(dg_ceil_div(HW, 32), dg_ceil_div(C, 32), B), block(32, 8);
-  nhwc_to_nchw_kernel<<<grid, block, 0, stream>>>((const bf16*)x, y, HW, C);
+  dg_launch(nhwc_to_nchw_kernel, dg_cfg(grid, block, 0, stream), (const bf16*)x, y, HW, C);
   DG_CHECK_LAUNCH("nhwc_to_nchw");
   return DG_OK;
 }
 int dg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int HW, int C, cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && HW > 0 && C > 0 && B <= 65535, "nchw_to_nhwc: bad dims");
   dim3 grid(dg_ceil_div(HW, 32), dg_ceil_div(C, 32), B), block(32, 8);
-  nchw_to_nhwc_kernel<<<grid, block, 0, stream>>>(x, (bf16*)y, HW, C);
+  dg_launch(nchw_to_nhwc_kernel, dg_cfg(grid, block, 0, stream), x, (bf16*)y, HW, C);
   DG_CHECK_LAUNCH("nchw_to_nhwc");
   return DG_OK;
 }
@@ -848,11 +894,11 @@ int dg_bn_stats(const void* z, long long P, int C, const float* gamma, const flo
   float* pq = scratch + (size_t)g.gy * C;
   dim3 grid(g.gx, g.gy);
   if (vec == 8)
-    bn_stats_partial_kernel<8><<<grid, 256, 0, stream>>>((const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq);
+    dg_launch(bn_stats_partial_kernel<8>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq);
   else
-    bn_stats_partial_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq);
+    dg_launch(bn_stats_partial_kernel<1>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq);
   DG_CHECK_LAUNCH("bn_stats_partial");
-  bn_stats_finalize_kernel<<<dg_ceil_div(C, 32), 256, 0, stream>>>(ps, pq, g.gy, P, C, eps, momentum, gamma, beta,
+  dg_launch(bn_stats_finalize_kernel, dg_cfg(dg_ceil_div(C, 32), 256, 0, stream), ps, pq, g.gy, P, C, eps, momentum, gamma, beta,
                                                                     stats, stats + C, stats + 2 * C, stats + 3 * C,
                                                                     running_mean, running_var);
   DG_CHECK_LAUNCH("bn_stats_finalize");
@@ -865,7 +911,7 @@ int dg_bn_stats_finalize(const float* part, int rows, long long P, int C, const 
                          float eps, float momentum, float* stats, float* running_mean, float* running_var,
                          cudaStream_t stream) {
   DG_CHECK_ARG(part && rows > 0 && P > 0 && C > 0 && stats, "bn_stats_finalize: bad args");
-  bn_stats_finalize_kernel<<<dg_ceil_div(C, 32), 256, 0, stream>>>(part, part + (size_t)rows * C, rows, P, C, eps,
+  dg_launch(bn_stats_finalize_kernel, dg_cfg(dg_ceil_div(C, 32), 256, 0, stream), part, part + (size_t)rows * C, rows, P, C, eps,
                                                                    momentum, gamma, beta, stats, stats + C,
                                                                    stats + 2 * C, stats + 3 * C, running_mean,
                                                                    running_var);
@@ -876,7 +922,7 @@ int dg_bn_stats_finalize(const float* part, int rows, long long P, int C, const 
 int dg_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                       float eps, int C, float* stats, cudaStream_t stream) {
   DG_CHECK_ARG(C > 0 && stats, "bn_eval_coeffs: bad args");
-  bn_eval_coeffs_kernel<<<dg_ceil_div(C, 128), 128, 0, stream>>>(gamma, beta, running_mean, running_var, eps, C,
+  dg_launch(bn_eval_coeffs_kernel, dg_cfg(dg_ceil_div(C, 128), 128, 0, stream), gamma, beta, running_mean, running_var, eps, C,
                                                                  stats + 2 * C, stats + 3 * C);
   DG_CHECK_LAUNCH("bn_eval_coeffs");
   return DG_OK;
@@ -890,10 +936,10 @@ int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats
   BnGeom g = bn_geom(P, C, vec, sms(), 8);
   dim3 grid(g.gx, g.gy);
   if (vec == 8)
-    bn_act_fwd_kernel<8><<<grid, 256, 0, stream>>>((const bf16*)z, (bf16*)y, P, C, g.cw, g.rows_iter, g.rows_split,
+    dg_launch(bn_act_fwd_kernel<8>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, (bf16*)y, P, C, g.cw, g.rows_iter, g.rows_split,
                                                    stats + 2 * C, stats + 3 * C, act, slope);
   else
-    bn_act_fwd_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)z, (bf16*)y, P, C, g.cw, g.rows_iter, g.rows_split,
+    dg_launch(bn_act_fwd_kernel<1>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, (bf16*)y, P, C, g.cw, g.rows_iter, g.rows_split,
                                                    stats + 2 * C, stats + 3 * C, act, slope);
   DG_CHECK_LAUNCH("bn_act_fwd");
   return DG_OK;
@@ -915,25 +961,25 @@ int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bca
   dim3 grid(g.gx, g.gy);
   const float* invstd = stats + C;
   if (vec == 8)
-    bn_bwd_partial_kernel<8><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
+    dg_launch(bn_bwd_partial_kernel<8>, dg_cfg(grid, 256, 0, stream), (const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
                                                        (const bf16*)z, stats, P, C, g.cw, g.rows_iter, g.rows_split, act,
                                                        slope, pg, pgx);
   else
-    bn_bwd_partial_kernel<1><<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
+    dg_launch(bn_bwd_partial_kernel<1>, dg_cfg(grid, 256, 0, stream), (const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
                                                        (const bf16*)z, stats, P, C, g.cw, g.rows_iter, g.rows_split, act,
                                                        slope, pg, pgx);
   DG_CHECK_LAUNCH("bn_bwd_partial");
-  bn_bwd_finalize_kernel<<<dg_ceil_div(C, 32), 256, 0, stream>>>(pg, pgx, g.gy, P, C, gamma, invstd, dgamma, dbeta,
+  dg_launch(bn_bwd_finalize_kernel, dg_cfg(dg_ceil_div(C, 32), 256, 0, stream), pg, pgx, g.gy, P, C, gamma, invstd, dgamma, dbeta,
                                                                  grad_beta, coefs);
   DG_CHECK_LAUNCH("bn_bwd_finalize");
   BnGeom g2 = bn_geom(P, C, vec, sms(), 8);
   dim3 grid2(g2.gx, g2.gy);
   if (vec == 8)
-    bn_bwd_dx_kernel<8><<<grid2, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
+    dg_launch(bn_bwd_dx_kernel<8>, dg_cfg(grid2, 256, 0, stream), (const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
                                                    (const bf16*)z, stats, coefs, (bf16*)dz, P, C, g2.cw, g2.rows_iter,
                                                    g2.rows_split, act, slope);
   else
-    bn_bwd_dx_kernel<1><<<grid2, 256, 0, stream>>>((const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
+    dg_launch(bn_bwd_dx_kernel<1>, dg_cfg(grid2, 256, 0, stream), (const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
                                                    (const bf16*)z, stats, coefs, (bf16*)dz, P, C, g2.cw, g2.rows_iter,
                                                    g2.rows_split, act, slope);
   DG_CHECK_LAUNCH("bn_bwd_dx");
@@ -943,27 +989,27 @@ int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bca
 int dg_gan_bce_fwd(const float* logit_real, const float* logit_fake, int B, float* p_real, float* p_fake, float* out2,
                    cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && logit_real && logit_fake && p_real && p_fake && out2, "gan_bce_fwd: bad args");
-  gan_bce_fwd_kernel<<<1, 256, 0, stream>>>(logit_real, logit_fake, B, p_real, p_fake, out2);
+  dg_launch(gan_bce_fwd_kernel, dg_cfg(1, 256, 0, stream), logit_real, logit_fake, B, p_real, p_fake, out2);
   DG_CHECK_LAUNCH("gan_bce_fwd");
   return DG_OK;
 }
 int dg_gan_bce_bwd(const float* p_real, const float* p_fake, int B, float g_dis, float g_gen, float* dlogit_real,
                    float* dlogit_fake, cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && p_real && p_fake, "gan_bce_bwd: bad args");
-  gan_bce_bwd_kernel<<<dg_ceil_div(B, 128), 128, 0, stream>>>(p_real, p_fake, B, g_dis, g_gen, dlogit_real,
+  dg_launch(gan_bce_bwd_kernel, dg_cfg(dg_ceil_div(B, 128), 128, 0, stream), p_real, p_fake, B, g_dis, g_gen, dlogit_real,
                                                               dlogit_fake);
   DG_CHECK_LAUNCH("gan_bce_bwd");
   return DG_OK;
 }
 int dg_sigmoid_fwd(const float* x, float* y, int n, cudaStream_t stream) {
   DG_CHECK_ARG(n > 0, "sigmoid_fwd: bad args");
-  sigmoid_fwd_kernel<<<dg_ceil_div(n, 128), 128, 0, stream>>>(x, y, n);
+  dg_launch(sigmoid_fwd_kernel, dg_cfg(dg_ceil_div(n, 128), 128, 0, stream), x, y, n);
   DG_CHECK_LAUNCH("sigmoid_fwd");
   return DG_OK;
 }
 int dg_sigmoid_bwd(const float* y, const float* dy, float* dx, int n, cudaStream_t stream) {
   DG_CHECK_ARG(n > 0, "sigmoid_bwd: bad args");
-  sigmoid_bwd_kernel<<<dg_ceil_div(n, 128), 128, 0, stream>>>(y, dy, dx, n);
+  dg_launch(sigmoid_bwd_kernel, dg_cfg(dg_ceil_div(n, 128), 128, 0, stream), y, dy, dx, n);
   DG_CHECK_LAUNCH("sigmoid_bwd");
   return DG_OK;
 }
@@ -975,16 +1021,16 @@ int dg_mse_fwd(const float* a, const float* b, long long n, float* out, float* s
   DG_CHECK_ARG(n > 0 && a && b && out && scratch, "mse_fwd: bad args");
   DG_CHECK_ARG(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0, "mse_fwd: inputs must be 16-byte aligned");
   const int grid = ew_grid(n / 4 + 1, sms());
-  mse_partial_kernel<<<grid, 256, 0, stream>>>(a, b, n, scratch);
+  dg_launch(mse_partial_kernel, dg_cfg(grid, 256, 0, stream), a, b, n, scratch);
   DG_CHECK_LAUNCH("mse_partial");
-  sum_finalize_kernel<<<1, 32, 0, stream>>>(scratch, grid, 1.0 / (double)n, out, 0);
+  dg_launch(sum_finalize_kernel, dg_cfg(1, 32, 0, stream), scratch, grid, 1.0 / (double)n, out, 0);
   DG_CHECK_LAUNCH("mse_finalize");
   return DG_OK;
 }
 // da (+)= g * 2/n * (a-b)
 int dg_mse_bwd(const float* a, const float* b, long long n, float g, float* da, int accumulate, cudaStream_t stream) {
   DG_CHECK_ARG(n > 0 && a && b && da, "mse_bwd: bad args");
-  mse_bwd_kernel<<<ew_grid(n, sms()), 256, 0, stream>>>(a, b, n, g * 2.f / (float)n, da, accumulate);
+  dg_launch(mse_bwd_kernel, dg_cfg(ew_grid(n, sms()), 256, 0, stream), a, b, n, g * 2.f / (float)n, da, accumulate);
   DG_CHECK_LAUNCH("mse_bwd");
   return DG_OK;
 }
@@ -994,16 +1040,16 @@ int dg_fm_fwd(const void* real, const void* fake, int B, long long n, float* dif
               float* scratch, cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && n > 0 && n % 8 == 0 && real && fake && out && scratch, "fm_fwd: bad args (n must be a multiple of 8)");
   const int grid = ew_grid(n / 8, sms());
-  fm_partial_kernel<<<grid, 256, 0, stream>>>((const bf16*)real, (const bf16*)fake, B, n, diff, scratch);
+  dg_launch(fm_partial_kernel, dg_cfg(grid, 256, 0, stream), (const bf16*)real, (const bf16*)fake, B, n, diff, scratch);
   DG_CHECK_LAUNCH("fm_partial");
-  sum_finalize_kernel<<<1, 32, 0, stream>>>(scratch, grid, 1.0 / (double)n, out, accumulate);
+  dg_launch(sum_finalize_kernel, dg_cfg(1, 32, 0, stream), scratch, grid, 1.0 / (double)n, out, accumulate);
   DG_CHECK_LAUNCH("fm_finalize");
   return DG_OK;
 }
 // dfeat_fake[b][i] = -g * 2/(n*B) * diff[i]   (use +g for the real branch)
 int dg_fm_bwd(const float* diff, int B, long long n, float g, void* dfeat, cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && n > 0 && n % 8 == 0 && diff && dfeat, "fm_bwd: bad args");
-  fm_bwd_kernel<<<ew_grid(n / 8, sms()), 256, 0, stream>>>(diff, B, n, -g * 2.f / ((float)n * (float)B), (bf16*)dfeat);
+  dg_launch(fm_bwd_kernel, dg_cfg(ew_grid(n / 8, sms()), 256, 0, stream), diff, B, n, -g * 2.f / ((float)n * (float)B), (bf16*)dfeat);
   DG_CHECK_LAUNCH("fm_bwd");
   return DG_OK;
 }
@@ -1014,9 +1060,9 @@ int dg_adam_step(float* p, const float* g, float* m, float* v, long long n, floa
                  float eps, float weight_decay, float* state, float grad_scale, cudaStream_t stream) {
   DG_CHECK_ARG(n > 0 && n % 4 == 0 && p && g && m && v && state, "adam_step: bad args (n must be a multiple of 4)");
   DG_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam_step: unaligned buffers");
-  adam_tick_kernel<<<1, 1, 0, stream>>>(state, beta1, beta2);
+  dg_launch(adam_tick_kernel, dg_cfg(1, 1, 0, stream), state, beta1, beta2);
   DG_CHECK_LAUNCH("adam_tick");
-  adam_kernel<<<ew_grid(n / 4, sms()), 256, 0, stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, lr,
+  dg_launch(adam_kernel, dg_cfg(ew_grid(n / 4, sms()), 256, 0, stream), (float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, lr,
                                                          beta1, beta2, eps, weight_decay, state, grad_scale);
   DG_CHECK_LAUNCH("adam_step");
   return DG_OK;
