@@ -275,6 +275,75 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on one TPC issue one M=256 MMA; each holds its 128 rows of A, half
+// of the N rows of B and its 128 accumulator lanes.  A kernel must use one cta_group value throughout. ----
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {   // one warp of EACH CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// issued by the leader CTA (cluster rank 0) only; descriptors are offsets valid in both CTAs' shared memory
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// TMA loads of a CTA pair: data lands in the executing CTA, the transaction bytes are counted on the LEADER's mbarrier
+// (same offset, peer bit of the shared::cluster address cleared)
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem, const void* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2cta(void* smem, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2cta(void* smem, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6, %7}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4)
+      : "memory");
+}
+// arrive on the mbarrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane_base + t).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
   asm volatile(

@@ -56,6 +56,12 @@ struct ConvGemmParams {
                       // accumulators (sum, sum of squares) over the rows this CTA produced; NULL = off
   int splits, kps;    // split-K: work item = (tile, split); a split covers K-iterations [split*kps, (split+1)*kps)
   float* ws;          // split-K: fp32 [output pixels][N] accumulator (zeroed by the launcher), NULL when splits == 1
+  int nacc;           // K-interleaved accumulators per tile (1, 2 or 4; nacc * block_n <= 256): back-to-back tcgen05.mma
+                      // into ONE accumulator serialise on its read-modify-write, which a narrow (N <= 128) MMA is too
+                      // short to hide; the k-substeps of a stage round-robin over nacc column blocks that the
+                      // epilogue sums
+  int debug;          // timing experiments (env DG_GEMM_DEBUG, results are garbage): 1 = no MMAs, 2 = no A loads,
+                      // 3 = no B loads, 4 = no loads at all
 };
 
 // Sum the 32 values each lane holds for 32 columns over the 32 lanes (rows) of the warp: afterwards v[0] of lane l is
@@ -96,13 +102,39 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
   return t;
 }
 
+// 32 accumulator columns of this thread's row, summed over the K-interleaved accumulators
+__device__ __forceinline__ void load_acc32(uint32_t taddr, int c, int nacc, int block_n, uint32_t (&r)[32]) {
+  tmem_ld_32x32(taddr + c, r);
+  tmem_ld_wait();
+  for (int j = 1; j < nacc; ++j) {
+    uint32_t t[32];
+    tmem_ld_32x32(taddr + j * block_n + c, t);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(t[e]));
+  }
+}
+
+// tile index of a work unit: unit u of a CTA pair = M tiles (2*mp, 2*mp+1) of N tile nt, u = mp * n_tiles + nt
+template <int kCta>
+__device__ __forceinline__ int unit_tile(const ConvGemmParams& p, int u, uint32_t crank) {
+  if (kCta == 1) return u;
+  const int nt = u % p.n_tiles, mp = u / p.n_tiles;
+  return (2 * mp + (int)crank) * p.n_tiles + nt;
+}
+
+// kCta = 2: launched as clusters of two CTAs that own two consecutive 128-row M tiles of the same N tile; one
+// tcgen05.mma.cta_group::2 (M = 256) issued by the leader feeds both.  Each CTA loads its own A tile and HALF of the B
+// rows, so the bytes an SM has to ingest per FLOP drop from (128+N) to (128+N/2) rows per k-step -- the L2->SM path is
+// what bounds these GEMMs.
+template <int kCta>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  const int stage_bytes = kATileBytes + p.block_n * 128;
+  const int stage_bytes = kATileBytes + (p.block_n / kCta) * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
   uint64_t* full_bar = bars;                    // [stages]
   uint64_t* empty_bar = bars + kMaxStages;      // [stages]
@@ -113,6 +145,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = kCta == 2 ? cluster_ctarank() : 0u;
+  // work units: (tile, split) for one CTA, (pair of M tiles, split) for a CTA pair
+  const int unit0 = kCta == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = kCta == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int unit_tiles = p.num_tiles / kCta;
+  const int num_units = unit_tiles * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -123,14 +161,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 4 * kCta);   // the leader's MMA thread waits for the epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) {
+    if (kCta == 2)
+      tmem_alloc_2cta(tmem_slot, kTmemCols);
+    else
+      tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (kCta == 2) cluster_sync_all();   // both CTAs' barriers and TMEM exist before any cross-CTA traffic
   // programmatic dependent launch: dependents may be scheduled once every CTA of this grid holds its TMEM columns;
   // nothing above touches global memory, everything below runs after the predecessor grid has completed
   griddep_launch_dependents();
@@ -141,9 +185,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < p.num_tiles * p.splits; w += gridDim.x) {
-        const TileCoord t = decode_tile(p, w % p.num_tiles);
-        const int k_begin = (w / p.num_tiles) * p.kps, k_end = min(p.k_iters, k_begin + p.kps);
+      const int nrow0 = (int)crank * (p.block_n / kCta);   // this CTA's share of the B rows
+      for (int w = unit0; w < num_units; w += unit_stride) {
+        const TileCoord t = decode_tile(p, unit_tile<kCta>(p, w % unit_tiles, crank));
+        const int k_begin = (w / unit_tiles) * p.kps, k_end = min(p.k_iters, k_begin + p.kps);
         const int py = t.par >> 1, px = t.par & 1;
         for (int it = k_begin; it < k_end; ++it) {
           const int tap_i = it / p.cpk;
@@ -151,21 +196,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kATileBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          // pair: the leader's barrier counts the bytes of both CTAs' loads
+          const bool la = p.debug != 2 && p.debug != 4, lb = p.debug != 3 && p.debug != 4;   // timing experiments
+          if (crank == 0) {
+            const uint32_t bytes = (la ? kATileBytes : 0) + (lb ? (uint32_t)(stage_bytes - kATileBytes) : 0);
+            if (bytes)
+              mbar_arrive_expect_tx(&full_bar[stage], bytes * kCta);
+            else
+              mbar_arrive(&full_bar[stage]);
+          }
           if (p.mode == 0) {
             const int kh = tap_i >> 2, kw = tap_i & 3;
             const int dh = ((kh + 1) >> 1) - 1, ph = (kh + 1) & 1;
             const int dw = ((kw + 1) >> 1) - 1, pw = (kw + 1) & 1;
-            tma_load_5d(sa, &tmA, &full_bar[stage], pw * p.Ck + c0, t.w0 + dw, ph, t.h0 + dh, t.b0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], tap_i * p.Ck + c0, t.nt * p.block_n);
+            if (kCta == 2) {
+              if (la) tma_load_5d_2cta(sa, &tmA, &full_bar[stage], pw * p.Ck + c0, t.w0 + dw, ph, t.h0 + dh, t.b0);
+              if (lb) tma_load_2d_2cta(sb, &tmB, &full_bar[stage], tap_i * p.Ck + c0, t.nt * p.block_n + nrow0);
+            } else {
+              if (la) tma_load_5d(sa, &tmA, &full_bar[stage], pw * p.Ck + c0, t.w0 + dw, ph, t.h0 + dh, t.b0);
+              if (lb) tma_load_2d(sb, &tmB, &full_bar[stage], tap_i * p.Ck + c0, t.nt * p.block_n);
+            }
           } else {
             const int th = tap_i >> 1, tw = tap_i & 1;
             const int kh = py == 0 ? (th ? 3 : 1) : (th ? 2 : 0);
             const int di = py == 0 ? (th ? -1 : 0) : (th ? 0 : 1);
             const int kw = px == 0 ? (tw ? 3 : 1) : (tw ? 2 : 0);
             const int dj = px == 0 ? (tw ? -1 : 0) : (tw ? 0 : 1);
-            tma_load_4d(sa, &tmA, &full_bar[stage], c0, t.w0 + dj, t.h0 + di, t.b0);
-            tma_load_2d(sb, &tmB, &full_bar[stage], (kh * 4 + kw) * p.Ck + c0, t.nt * p.block_n);
+            if (kCta == 2) {
+              if (la) tma_load_4d_2cta(sa, &tmA, &full_bar[stage], c0, t.w0 + dj, t.h0 + di, t.b0);
+              if (lb) tma_load_2d_2cta(sb, &tmB, &full_bar[stage], (kh * 4 + kw) * p.Ck + c0, t.nt * p.block_n + nrow0);
+            } else {
+              if (la) tma_load_4d(sa, &tmA, &full_bar[stage], c0, t.w0 + dj, t.h0 + di, t.b0);
+              if (lb) tma_load_2d(sb, &tmB, &full_bar[stage], (kh * 4 + kw) * p.Ck + c0, t.nt * p.block_n);
+            }
           }
           if (++stage == p.num_stages) {
             stage = 0;
@@ -175,8 +238,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+    if (lane == 0 && crank == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM * kCta, p.block_n, 0, 0);
       // descriptors differ only in the 14-bit start-address field: build the constant part once and add the
       // (stage, k) offset per MMA so the single issuing thread spends a handful of instructions per tcgen05.mma
       const uint64_t desc_base = make_sdesc_sw128(0, 16, 1024);
@@ -185,8 +248,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < p.num_tiles * p.splits; w += gridDim.x) {
-        const int k_begin = (w / p.num_tiles) * p.kps, k_end = min(p.k_iters, k_begin + p.kps);
+      for (int w = unit0; w < num_units; w += unit_stride) {
+        const int k_begin = (w / unit_tiles) * p.kps, k_end = min(p.k_iters, k_begin + p.kps);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
@@ -197,15 +260,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t da0 = desc_base | (uint64_t)((sa & 0x3FFFFu) >> 4);
           const uint64_t db0 = desc_base | (uint64_t)(((sa + kATileBytes) & 0x3FFFFu) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(d_tmem, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (it > k_begin || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if (p.debug == 1) break;
+            const int j = k & (p.nacc - 1);   // accumulator of this k-substep
+            const uint32_t accum = (it > k_begin || k >= p.nacc) ? 1u : 0u;
+            const uint32_t d = d_tmem + (uint32_t)(j * p.block_n);
+            if (kCta == 2)
+              umma_bf16_2cta(d, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, accum);
+            else
+              umma_bf16(d, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, accum);
+          }
+          if (kCta == 2)
+            umma_commit_2cta(&empty_bar[stage], 3);   // frees the stage in both CTAs
+          else
+            umma_commit(&empty_bar[stage]);
           if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (kCta == 2)
+          umma_commit_2cta(&tfull_bar[acc], 3);
+        else
+          umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -220,8 +297,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = threadIdx.x - 64; i < 2 * p.N; i += 128) s_stat[i] = 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    for (int w = blockIdx.x; w < p.num_tiles * p.splits; w += gridDim.x) {
-      const TileCoord t = decode_tile(p, w % p.num_tiles);
+    for (int w = unit0; w < num_units; w += unit_stride) {
+      const TileCoord t = decode_tile(p, unit_tile<kCta>(p, w % unit_tiles, crank));
       const int wl = row % p.Wt;
       const int hl = (row / p.Wt) % p.Ht;
       const int bl = row / (p.Wt * p.Ht);
@@ -259,8 +336,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float* wrow = p.ws + opix * p.N + (size_t)t.nt * p.block_n;
         for (int c = 0; c < p.block_n; c += 32) {
           uint32_t r[32];
-          tmem_ld_32x32(taddr + c, r);
-          tmem_ld_wait();
+          load_acc32(taddr, c, p.nacc, p.block_n, r);
           if (valid) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -288,8 +364,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bf16* mrow = p.mask ? p.mask + opix * p.N + (size_t)t.nt * p.block_n : nullptr;
         for (int c = 0; c < p.block_n; c += 32) {
           uint32_t r[32];
-          tmem_ld_32x32(taddr + c, r);
-          tmem_ld_wait();
+          load_acc32(taddr, c, p.nacc, p.block_n, r);
           if (p.stat_part) {   // rows beyond the batch are exact zeros (TMA zero fill), so no masking is needed
             float v[32];
 #pragma unroll
@@ -331,7 +406,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (kCta == 2)
+          mbar_arrive_cluster(&tempty_bar[acc], 0);   // the accumulator stage is reused by the leader's MMA thread
+        else
+          mbar_arrive(&tempty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -348,9 +428,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if (kCta == 2) cluster_sync_all();   // the pair's MMAs, commits and remote arrivals are all done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kCta == 2)
+      tmem_dealloc_2cta(tmem_base, kTmemCols);
+    else
+      tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -657,6 +741,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 // split-K workspace registered by the host (dg_conv_set_splitk_workspace); split-K is off without it
 float* g_splitk_ws = nullptr;
 size_t g_splitk_ws_bytes = 0;
+// test hooks (dg_conv_set_tiling): force the N tile (0 = heuristic) and switch CTA pairs (-1 = default / DG_GEMM_PAIR)
+int g_force_bn = 0;
+int g_force_pair = -1;
 
 struct ConvGemmExtras {
   const void* mask = nullptr;
@@ -692,12 +779,35 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   p.cpk = p.Ck / 64;
   p.k_iters = (mode == 0 ? 16 : 4) * p.cpk;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b * (mode == 0 ? 1 : 4);
+  // N tile: measured cost of one k-iteration of a 128 x bn x 64 tile is ~{904, 782, 678} cycles for bn = {256, 128, 64}
+  // on every layer shape (profiles/README.md), i.e. wide tiles are worth more than filling the last SMs: pick the bn
+  // that minimises waves(bn) * cost(bn) on the persistent grid
   int bn = img_mode ? 16 : 64;
-  const int cands[3] = {256, 128, 64};
-  for (int i = 0; i < 3 && !img_mode; ++i) {
-    if (N % cands[i]) continue;
-    bn = cands[i];
-    if ((long long)m_tiles * (N / bn) >= num_sms()) break;
+  static int bn_policy = -1;   // DG_GEMM_BNPOLICY=0: round-1 rule (smallest tile count that still fills the SMs), A/B only
+  if (bn_policy < 0) {
+    const char* e = getenv("DG_GEMM_BNPOLICY");
+    bn_policy = e ? atoi(e) : 1;
+  }
+  if (!img_mode && bn_policy == 0) {
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      if (N % cands[i]) continue;
+      bn = cands[i];
+      if ((long long)m_tiles * (N / bn) >= num_sms()) break;
+    }
+  } else if (!img_mode) {
+    const int cands[3] = {256, 128, 64};
+    const int cost[3] = {904, 782, 678};
+    long long best = -1;
+    for (int i = 0; i < 3; ++i) {
+      if (N % cands[i]) continue;
+      const long long tiles = (long long)m_tiles * (N / cands[i]);
+      const long long t = ((tiles + num_sms() - 1) / num_sms()) * cost[i];
+      if (best < 0 || t < best) {
+        best = t;
+        bn = cands[i];
+      }
+    }
   }
   // SM-starved big GEMMs (few M tiles, long K): prefer the widest N tile (best bytes/FLOP) and fill the machine with
   // split-K instead of shrinking the tile
@@ -706,6 +816,7 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   if (!img_mode && !ex.mask && g_splitk_ws && gflop_all > 16.0 && k_iters_all >= 64 && N % 256 == 0 &&
       (long long)m_tiles * (N / 256) * 2 <= num_sms())
     bn = 256;
+  if (g_force_bn && !img_mode && N % g_force_bn == 0) bn = g_force_bn;
   p.block_n = bn;
   p.n_tiles = N / bn;
   p.num_tiles = m_tiles * p.n_tiles;
@@ -723,6 +834,19 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   p.splits = 1;
   p.kps = p.k_iters;
   p.ws = nullptr;
+  static int debug_mode = -1;
+  if (debug_mode < 0) {
+    const char* e = getenv("DG_GEMM_DEBUG");
+    debug_mode = e ? atoi(e) : 0;
+  }
+  p.debug = debug_mode;
+  static int nacc_mode = -1;
+  if (nacc_mode < 0) {
+    const char* e = getenv("DG_GEMM_NACC");
+    nacc_mode = e ? atoi(e) : 4;
+  }
+  p.nacc = 1;
+  while (!img_mode && p.nacc * 2 <= nacc_mode && p.nacc * 2 * bn <= kAccStride) p.nacc *= 2;
   const double gflop = 2.0 * B * Hs * Ws * (double)Cs * Cb * 16 * 1e-9;
   const size_t ws_need = (size_t)B * p.Ho * p.Wo * N * sizeof(float);
   if (!img_mode && !ex.mask && g_splitk_ws && ws_need <= g_splitk_ws_bytes && gflop > 16.0 &&
@@ -735,8 +859,19 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
       p.ws = g_splitk_ws;
     }
   }
-  const int work = p.num_tiles * p.splits;
-  const int grid = work < num_sms() ? work : num_sms();
+  // CTA pairs (cta_group::2) whenever two consecutive M tiles of one parity plane exist and half an N tile is still
+  // a whole number of 64-row TMA boxes
+  static int pair_mode = -1;
+  if (pair_mode < 0) {
+    const char* e = getenv("DG_GEMM_PAIR");
+    pair_mode = e ? atoi(e) : 1;
+  }
+  const int tiles_per_plane = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int want_pair = g_force_pair >= 0 ? g_force_pair : pair_mode;
+  const int ncta = (want_pair && !img_mode && bn >= 128 && tiles_per_plane % 2 == 0) ? 2 : 1;
+  const int work = (p.num_tiles / ncta) * p.splits;
+  const int max_units = num_sms() / ncta;
+  const int grid = (work < max_units ? work : max_units) * ncta;
   if (ex.grid_out) {
     *ex.grid_out = p.ws ? 0 : grid;   // 0: statistics cannot be fused for this shape (split-K)
     return DG_OK;
@@ -745,7 +880,7 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     DG_CHECK_ARG(ex.stat_part == nullptr, "conv gemm: fused statistics requested for a split-K shape");
     cudaMemsetAsync(p.ws, 0, ws_need, stream);
   }
-  const int stage_bytes = kATileBytes + bn * 128;
+  const int stage_bytes = kATileBytes + (bn / ncta) * 128;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
@@ -757,23 +892,28 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   if (mode == 0) {
     rc = make_parity_map(&tmA, a, B, 2 * Hs, 2 * Ws, Cb, p.Wt, p.Ht, p.Bt);
     if (rc) return rc;
-    rc = make_weight_map(&tmB, wpacked, Cs, 16 * Cb, bn);
+    rc = make_weight_map(&tmB, wpacked, Cs, 16 * Cb, bn / ncta);
   } else {
     rc = make_nhwc_map(&tmA, a, B, Hs, Ws, Cs, p.Wt, p.Ht, p.Bt);
     if (rc) return rc;
-    rc = make_weight_map(&tmB, wpacked, Cb, 16 * Cs, bn);
+    rc = make_weight_map(&tmB, wpacked, Cb, 16 * Cs, bn / ncta);
   }
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       dg_set_error("conv gemm: cannot raise dynamic smem: %s", cudaGetErrorString(e));
       return DG_ERR_CUDA;
     }
     attr_set = true;
   }
-  dg_launch(conv_gemm_kernel, dg_cfg(grid, kThreads, smem_bytes, stream), tmA, tmB, p);
+  if (ncta == 2)
+    dg_launch(conv_gemm_kernel<2>, dg_cfg(grid, kThreads, smem_bytes, stream, 2), tmA, tmB, p);
+  else
+    dg_launch(conv_gemm_kernel<1>, dg_cfg(grid, kThreads, smem_bytes, stream), tmA, tmB, p);
   DG_CHECK_LAUNCH("conv_gemm_kernel");
   if (p.ws) {
     const long long n8 = (long long)(ws_need / sizeof(float)) / 8;
@@ -826,6 +966,13 @@ int dg_conv4x4s2_dgrad(const void* dz, const void* wu, void* dx, int B, int Hs, 
 
 // Register a device workspace for split-K (fp32 [output pixels][N] of the largest split layer; 64 MB covers the
 // 512x512 family).  NULL/0 disables split-K.  The buffer is used by launches on any stream in program order.
+int dg_conv_set_tiling(int block_n, int pair) {
+  DG_CHECK_ARG(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 256, "conv tiling: block_n=%d", block_n);
+  g_force_bn = block_n;
+  g_force_pair = pair;
+  return DG_OK;
+}
+
 int dg_conv_set_splitk_workspace(void* ws, size_t bytes) {
   g_splitk_ws = reinterpret_cast<float*>(ws);
   g_splitk_ws_bytes = ws ? bytes : 0;

@@ -89,6 +89,11 @@ _splitk_ws = {}
 _splitk_enabled = set()
 
 
+def set_conv_tiling(block_n=0, pair=-1):
+    """Test hook: force the GEMM N tile / CTA pairing of the conv kernels (0, -1 = heuristics)."""
+    check(lib().dg_conv_set_tiling(int(block_n), int(pair)), "dg_conv_set_tiling")
+
+
 def enable_splitk(device, nbytes=64 << 20):
     """Allow split-K for the SM-starved deep layers on this device (the trainer turns it on).  Each lane gets its own
     fp32 workspace; the pointer of the current lane is handed to the C library right before every GEMM launch."""

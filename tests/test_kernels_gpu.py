@@ -431,3 +431,45 @@ def test_conv_splitk_deep_layer():
     finally:
         ops._splitk_enabled.clear()
         ops._splitk_select(xn.device)
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("B,H,Cb,Cs", [(4, 16, 256, 256),     # 2 tiles per plane: one CTA pair per N tile
+                                       (6, 32, 256, 256),     # batch remainder inside the second tile of a pair
+                                       (2, 128, 256, 256),    # Wt < W: pairs of row segments
+                                       (32, 64, 128, 256)])   # what the heuristic itself pairs (bn = 256 / 128)
+def test_conv_cta_pairs(bn, B, H, Cb, Cs):
+    """CTA pairs (tcgen05 cta_group::2: two M tiles per MMA, each CTA loads half of the weight tile) give the same
+    result as single-CTA tiles, for every N tile, with and without fused statistics."""
+    ops = ops_mod()
+    x = rnd(B, Cb, H, H, seed=1).to(BF16)
+    w = (rnd(Cs, Cb, 4, 4, seed=2) / (4 * Cb ** 0.5)).to(BF16).float()
+    wd, wu = ops.pack_weights(w)
+    xn = to_nhwc_bf16(x.float())
+    s = rnd(B, Cs, H // 2, H // 2, seed=3).to(BF16)
+    sn = to_nhwc_bf16(s.float())
+    ref_d = F.conv2d(x.float(), w, stride=2, padding=1)
+    ref_u = F.conv_transpose2d(s.float(), w, stride=2, padding=1)
+    try:
+        ops.set_conv_tiling(bn, 0)
+        d1, u1 = ops.conv_down(xn, wd), ops.conv_up(sn, wu)
+        ops.set_conv_tiling(bn, 1)
+        d2, u2 = ops.conv_down(xn, wd), ops.conv_up(sn, wu)
+        z, part = ops.conv_down_stats(xn, wd)
+        zu, partu = ops.conv_up_stats(sn, wu)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_conv_tiling(0, -1)
+    assert rel_l2(to_nchw_f32(d2), ref_d) < 4e-3 and rel_l2(to_nchw_f32(u2), ref_u) < 4e-3
+    assert torch.equal(d1, d2) and torch.equal(u1, u2)          # same K order, same fp32 accumulation
+    assert torch.equal(z, d2) and torch.equal(zu, u2)
+    P = z.numel() // Cs
+    g, b = torch.ones(Cs, device="cuda"), torch.zeros(Cs, device="cuda")
+    st = ops.bn_stats_finalize(part, P, g, b)
+    ref = ops.bn_stats(z.view(P, Cs), g, b)
+    assert torch.allclose(st[0], ref[0], atol=3e-3, rtol=1e-2) and torch.allclose(st[1], ref[1], rtol=1e-2)
+    Pu = zu.numel() // Cb
+    gu, bu = torch.ones(Cb, device="cuda"), torch.zeros(Cb, device="cuda")
+    stu = ops.bn_stats_finalize(partu, Pu, gu, bu)
+    refu = ops.bn_stats(zu.view(Pu, Cb), gu, bu)
+    assert torch.allclose(stu[0], refu[0], atol=3e-3, rtol=1e-2) and torch.allclose(stu[1], refu[1], rtol=1e-2)

@@ -1,0 +1,39 @@
+"""Tile-shape sweep on the SM-starved deep layer (down 16->8, 1024->2048, B=32)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from discogan_modernized_b200 import ops  # noqa: E402
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / n
+
+
+for (B, H, Cb, Cs) in [(32, 16, 1024, 2048), (64, 16, 1024, 2048), (32, 32, 512, 1024), (32, 256, 64, 128)]:
+    big = torch.randn(B, H, H, Cb, device="cuda").to(torch.bfloat16)
+    small = torch.randn(B, H // 2, H // 2, Cs, device="cuda").to(torch.bfloat16)
+    w = torch.randn(Cs, Cb, 4, 4, device="cuda") * 0.01
+    wd, wu = ops.pack_weights(w)
+    fl = 2.0 * B * (H // 2) ** 2 * Cs * Cb * 16
+    for bn in (256, 128, 64):
+        for pair in (0, 1):
+            if bn > min(Cs, Cb):
+                continue
+            ops.set_conv_tiling(bn, pair)
+            md = timeit(lambda: ops.conv_down(big, wd))
+            mu = timeit(lambda: ops.conv_up(small, wu))
+            print(f"B{B} H{H} {Cb}->{Cs} bn={bn} pair={pair}: down {md * 1e3:.1f} us {fl / md / 1e9:.0f} TF | "
+                  f"up {mu * 1e3:.1f} us {fl / mu / 1e9:.0f} TF")
+    ops.set_conv_tiling(0, -1)
