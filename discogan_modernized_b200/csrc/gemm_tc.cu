@@ -61,7 +61,7 @@ struct ConvGemmParams {
                       // short to hide; the k-substeps of a stage round-robin over nacc column blocks that the
                       // epilogue sums
   int debug;          // timing experiments (env DG_GEMM_DEBUG, results are garbage): 1 = no MMAs, 2 = no A loads,
-                      // 3 = no B loads, 4 = no loads at all
+                      // 3 = no B loads, 4 = no loads at all, 5 = no loads and A operand from TMEM
 };
 
 // Sum the 32 values each lane holds for 32 columns over the 32 lanes (rows) of the warp: afterwards v[0] of lane l is
@@ -197,7 +197,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kATileBytes;
           // pair: the leader's barrier counts the bytes of both CTAs' loads
-          const bool la = p.debug != 2 && p.debug != 4, lb = p.debug != 3 && p.debug != 4;   // timing experiments
+          const bool la = p.debug != 2 && p.debug < 4, lb = p.debug != 3 && p.debug < 4;   // timing experiments
           if (crank == 0) {
             const uint32_t bytes = (la ? kATileBytes : 0) + (lb ? (uint32_t)(stage_bytes - kATileBytes) : 0);
             if (bytes)
@@ -267,6 +267,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t d = d_tmem + (uint32_t)(j * p.block_n);
             if (kCta == 2)
               umma_bf16_2cta(d, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, accum);
+            else if (p.debug == 5)   // timing experiment: A operand from (uninitialised) TMEM columns
+              umma_bf16_ts(d, tmem_base + 448u + (uint32_t)(8 * k), db0 + (uint64_t)(2 * k), idesc, accum);
             else
               umma_bf16(d, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, accum);
           }
@@ -843,7 +845,7 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   static int nacc_mode = -1;
   if (nacc_mode < 0) {
     const char* e = getenv("DG_GEMM_NACC");
-    nacc_mode = e ? atoi(e) : 4;
+    nacc_mode = e ? atoi(e) : 1;
   }
   p.nacc = 1;
   while (!img_mode && p.nacc * 2 <= nacc_mode && p.nacc * 2 * bn <= kAccStride) p.nacc *= 2;
@@ -868,7 +870,7 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   }
   const int tiles_per_plane = p.tiles_w * p.tiles_h * p.tiles_b;
   const int want_pair = g_force_pair >= 0 ? g_force_pair : pair_mode;
-  const int ncta = (want_pair && !img_mode && bn >= 128 && tiles_per_plane % 2 == 0) ? 2 : 1;
+  const int ncta = (want_pair && !img_mode && bn >= 64 && tiles_per_plane % 2 == 0) ? 2 : 1;
   const int work = (p.num_tiles / ncta) * p.splits;
   const int max_units = num_sms() / ncta;
   const int grid = (work < max_units ? work : max_units) * ncta;

@@ -558,6 +558,210 @@ bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Streaming variants of the three big BatchNorm passes for C <= 256 (the layers with the large P): [P, C] is contiguous,
+// so a tile of R rows is ONE 1-D bulk copy (cp.async.bulk -> shared memory, mbarrier completion).  Thread 0 keeps
+// kBsStages tiles of every input stream in flight per block, i.e. the bytes in flight no longer depend on registers or
+// occupancy -- the register-staged kernels above top out at 45-60 % of the HBM copy bandwidth because they cannot
+// keep more than ~32 KB per SM outstanding.  Threads read their 16-byte channel vector from the staged tile
+// (conflict-free: consecutive threads, consecutive 16 bytes) and store results straight to global memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBsTileBytes = 16384;
+constexpr int kBsStages = 3;
+enum { BS_FWD = 0, BS_BWD_PARTIAL = 1, BS_BWD_DX = 2 };
+
+struct BnStreamParams {
+  const bf16* in[3];   // FWD: {z}; BWD: {dy, z, dy2 or NULL}
+  int nstreams;
+  bf16* out;           // FWD: y, BWD_DX: dz
+  const float* bcast;  // optional broadcast gradient [bcast_rows][C] (fp32), added as coef * bcast[row % bcast_rows]
+  float bcast_coef;
+  long long bcast_rows;
+  const float* stats;  // {mean, invstd, scale, shift}[C]
+  const float* coefs;  // BWD_DX: {gamma*invstd, mean(g), mean(g*xhat)}[C]
+  float* part0;        // BWD_PARTIAL: per-block partial sums [gridDim.x][C]
+  float* part1;
+  long long P;
+  int C, rows_tile;
+  long long tiles;
+  int tiles_per_block;
+  int act;
+  float slope;
+};
+
+__device__ __forceinline__ void bulk_load_1d(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem)),
+               "l"(reinterpret_cast<uint64_t>(gmem)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bn_stream_kernel(const BnStreamParams p) {
+  griddep_launch_dependents();
+  griddep_wait();
+  extern __shared__ __align__(128) uint8_t bs_smem[];
+  __shared__ uint64_t full_bar[kBsStages];
+  const int C = p.C, cw = C >> 3, rows_iter = 256 / cw;
+  const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
+  const bool active = ty < rows_iter;
+  const int c = tx * 8;
+  const long long t0 = (long long)blockIdx.x * p.tiles_per_block;
+  const int ntiles = (int)min((long long)p.tiles_per_block, p.tiles - t0);
+  const int R = p.rows_tile;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kBsStages; ++s) mbar_init(&full_bar[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int i) {
+    const long long row0 = (t0 + i) * R;
+    const uint32_t bytes = (uint32_t)min((long long)R, p.P - row0) * (uint32_t)C * 2u;
+    const int s = i % kBsStages;
+    mbar_arrive_expect_tx(&full_bar[s], bytes * (uint32_t)p.nstreams);
+    for (int k = 0; k < p.nstreams; ++k)
+      bulk_load_1d(bs_smem + (size_t)(s * p.nstreams + k) * kBsTileBytes, p.in[k] + row0 * C, bytes, &full_bar[s]);
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < kBsStages && i < ntiles; ++i) issue(i);
+
+  // per-channel constants of this thread's 8 channels
+  float sc[8], sh[8], k0[8], a1[8], a0[8], mu[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = p.stats[2 * C + c + i];
+    sh[i] = p.stats[3 * C + c + i];
+    s1[i] = s2[i] = 0.f;
+    mu[i] = k0[i] = a1[i] = a0[i] = 0.f;
+    if (MODE == BS_BWD_PARTIAL) mu[i] = p.stats[c + i];
+    if (MODE == BS_BWD_DX) {
+      const float m = p.stats[c + i], is = p.stats[C + c + i];
+      k0[i] = p.coefs[c + i];
+      const float k1 = p.coefs[C + c + i], k2 = p.coefs[2 * C + c + i];
+      a1[i] = -k0[i] * k2 * is;                // dz = k0*(g' - k1 - (z-mu)*is*k2) = k0*g' + a1*z + a0
+      a0[i] = -k0[i] * k1 - a1[i] * m;
+    }
+  }
+
+  for (int i = 0; i < ntiles; ++i) {
+    const int s = i % kBsStages;
+    mbar_wait(&full_bar[s], (uint32_t)(i / kBsStages) & 1u);
+    const long long row0 = (t0 + i) * R;
+    const int rows = (int)min((long long)R, p.P - row0);
+    const uint8_t* st = bs_smem + (size_t)(s * p.nstreams) * kBsTileBytes;
+    if (active) {
+      for (int r = ty; r < rows; r += rows_iter) {
+        const size_t off = ((size_t)r * C + c) * 2;
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(st + off), f);
+        if (MODE == BS_FWD) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = act_fwd(f[k] * sc[k] + sh[k], p.act, p.slope);
+          *reinterpret_cast<bf16x8*>(p.out + (row0 + r) * C + c) = pack8(f);
+        } else {
+          float z[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(st + kBsTileBytes + off), z);
+          if (p.nstreams == 3) {
+            float t[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(st + 2 * kBsTileBytes + off), t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += t[k];
+          }
+          if (p.bcast) {
+            const float* bp = p.bcast + ((row0 + r) % p.bcast_rows) * C + c;
+            const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 4);
+            f[0] += p.bcast_coef * b0.x; f[1] += p.bcast_coef * b0.y; f[2] += p.bcast_coef * b0.z; f[3] += p.bcast_coef * b0.w;
+            f[4] += p.bcast_coef * b1.x; f[5] += p.bcast_coef * b1.y; f[6] += p.bcast_coef * b1.z; f[7] += p.bcast_coef * b1.w;
+          }
+          if (MODE == BS_BWD_PARTIAL) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float gg = f[k] * act_grad_from_out(z[k] * sc[k] + sh[k], p.act, p.slope);
+              s1[k] += gg;
+              s2[k] += gg * (z[k] - mu[k]);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float gg = f[k] * act_grad_from_out(z[k] * sc[k] + sh[k], p.act, p.slope);
+              f[k] = k0[k] * gg + a1[k] * z[k] + a0[k];
+            }
+            *reinterpret_cast<bf16x8*>(p.out + (row0 + r) * C + c) = pack8(f);
+          }
+        }
+      }
+    }
+    __syncthreads();   // every thread is done with stage s: refill it
+    if (threadIdx.x == 0 && i + kBsStages < ntiles) issue(i + kBsStages);
+  }
+  if (MODE == BS_BWD_PARTIAL) {
+    // block reduction over the row lanes in the (now idle) staging buffer; one partial row per block
+    float* sh1 = reinterpret_cast<float*>(bs_smem);
+    float* sh2 = sh1 + 256 * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sh1[threadIdx.x * 8 + k] = s1[k];
+      sh2[threadIdx.x * 8 + k] = active ? s2[k] * p.stats[C + c + k] : 0.f;   // xhat = (z - mean) * invstd
+    }
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float a = 0.f, b = 0.f;
+        for (int r = 0; r < rows_iter; ++r) {
+          a += sh1[(r * cw + tx) * 8 + k];
+          b += sh2[(r * cw + tx) * 8 + k];
+        }
+        p.part0[(size_t)blockIdx.x * C + c + k] = a;
+        p.part1[(size_t)blockIdx.x * C + c + k] = b;
+      }
+    }
+  }
+}
+
+// geometry of a streaming launch; returns false when the shape does not qualify
+struct BnStreamPlan {
+  int grid, tiles_per_block, rows_tile, smem;
+  long long tiles;
+};
+bool bn_stream_plan(long long P, int C, int nstreams, int sms, BnStreamPlan* pl) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DG_BN_STREAM");
+    mode = e ? atoi(e) : 1;
+  }
+  if (!mode || C % 8 != 0 || C > 256 || C < 8) return false;
+  if ((long long)P * C * 2 < (4LL << 20)) return false;   // small tensors are latency-bound: keep the light kernels
+  pl->rows_tile = kBsTileBytes / (C * 2);
+  pl->tiles = (P + pl->rows_tile - 1) / pl->rows_tile;
+  pl->smem = kBsStages * nstreams * kBsTileBytes;
+  const int per_sm = (224 * 1024) / (pl->smem + 2 * 1024);
+  long long blocks = (long long)sms * (per_sm < 1 ? 1 : (per_sm > 3 ? 3 : per_sm));
+  if (blocks > pl->tiles) blocks = pl->tiles;
+  pl->tiles_per_block = (int)((pl->tiles + blocks - 1) / blocks);
+  pl->grid = (int)((pl->tiles + pl->tiles_per_block - 1) / pl->tiles_per_block);
+  return true;
+}
+
+template <int MODE>
+int bn_stream_launch(const BnStreamParams& p, const BnStreamPlan& pl, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(bn_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) {
+      dg_set_error("bn stream: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+      return DG_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dg_launch(bn_stream_kernel<MODE>, dg_cfg(pl.grid, 256, pl.smem, stream), p);
+  DG_CHECK_LAUNCH("bn_stream_kernel");
+  return DG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // losses
 // ------------------------------------------------------------------------------------------------
@@ -880,7 +1084,8 @@ int dg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int HW, int C, cuda
 size_t dg_bn_scratch_floats(long long P, int C) {
   const int vec = (C % 8 == 0) ? 8 : 1;
   BnGeom g = bn_geom(P, C, vec, sms());
-  return (size_t)2 * g.gy * C;
+  const int rows = g.gy > 3 * sms() ? g.gy : 3 * sms();   // the streaming backward writes one partial row per block
+  return (size_t)2 * rows * C;
 }
 
 // Training-mode statistics of z[P][C]: mean, invstd, apply coefficients (scale, shift) and the running-stat update
@@ -932,6 +1137,22 @@ int dg_bn_eval_coeffs(const float* gamma, const float* beta, const float* runnin
 int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats, int act, float slope,
                   cudaStream_t stream) {
   DG_CHECK_ARG(P > 0 && C > 0 && z && y && stats, "bn_act_fwd: bad args");
+  BnStreamPlan pl;
+  if (((uintptr_t)z & 15) == 0 && ((uintptr_t)y & 15) == 0 && bn_stream_plan(P, C, 1, sms(), &pl)) {
+    BnStreamParams sp = {};
+    sp.in[0] = (const bf16*)z;
+    sp.nstreams = 1;
+    sp.out = (bf16*)y;
+    sp.stats = stats;
+    sp.P = P;
+    sp.C = C;
+    sp.rows_tile = pl.rows_tile;
+    sp.tiles = pl.tiles;
+    sp.tiles_per_block = pl.tiles_per_block;
+    sp.act = act;
+    sp.slope = slope;
+    return bn_stream_launch<BS_FWD>(sp, pl, stream);
+  }
   const int vec = (C % 8 == 0) ? 8 : 1;
   BnGeom g = bn_geom(P, C, vec, sms(), 8);
   dim3 grid(g.gx, g.gy);
@@ -954,6 +1175,36 @@ int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bca
   (void)y;  // the activation derivative is recomputed from z and the statistics; y is accepted for API symmetry
   DG_CHECK_ARG(P > 0 && C > 0 && dy && z && stats && dz && coefs && scratch, "bn_act_bwd: bad args");
   DG_CHECK_ARG(!bcast || bcast_rows > 0, "bn_act_bwd: bcast_rows must be positive");
+  BnStreamPlan pl;
+  if ((((uintptr_t)dy | (uintptr_t)dy2 | (uintptr_t)z | (uintptr_t)dz | (uintptr_t)bcast) & 15) == 0 &&
+      bn_stream_plan(P, C, dy2 ? 3 : 2, sms(), &pl)) {
+    BnStreamParams sp = {};
+    sp.in[0] = (const bf16*)dy;
+    sp.in[1] = (const bf16*)z;
+    sp.in[2] = (const bf16*)dy2;
+    sp.nstreams = dy2 ? 3 : 2;
+    sp.bcast = bcast;
+    sp.bcast_coef = bcast_coef;
+    sp.bcast_rows = bcast_rows;
+    sp.stats = stats;
+    sp.coefs = coefs;
+    sp.part0 = scratch;
+    sp.part1 = scratch + (size_t)pl.grid * C;
+    sp.P = P;
+    sp.C = C;
+    sp.rows_tile = pl.rows_tile;
+    sp.tiles = pl.tiles;
+    sp.tiles_per_block = pl.tiles_per_block;
+    sp.act = act;
+    sp.slope = slope;
+    int rc = bn_stream_launch<BS_BWD_PARTIAL>(sp, pl, stream);
+    if (rc) return rc;
+    dg_launch(bn_bwd_finalize_kernel, dg_cfg(dg_ceil_div(C, 32), 256, 0, stream), (const float*)sp.part0,
+              (const float*)sp.part1, pl.grid, P, C, gamma, stats + C, dgamma, dbeta, grad_beta, coefs);
+    DG_CHECK_LAUNCH("bn_bwd_finalize");
+    sp.out = (bf16*)dz;
+    return bn_stream_launch<BS_BWD_DX>(sp, pl, stream);
+  }
   const int vec = (C % 8 == 0) ? 8 : 1;
   BnGeom g = bn_geom(P, C, vec, sms());
   float* pg = scratch;

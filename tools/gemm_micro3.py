@@ -32,9 +32,9 @@ for (B, H, Cb, Cs) in [(32, 32, 512, 1024), (32, 256, 64, 128)]:
     for bn in (256, 128, 64):
         if bn > min(Cs, Cb):
             continue
-        ops.set_conv_tiling(bn, 0)
+        ops.set_conv_tiling(bn, int(os.environ.get("PAIR", "0")))
         md = timeit(lambda: ops.conv_down(big, wd))
         mu = timeit(lambda: ops.conv_up(small, wu))
-        print(f"debug={dbg} B{B} H{H} {Cb}->{Cs} bn={bn}: down {md * 1e3:.1f} us {fl / md / 1e9:.0f} TF | "
+        print(f"debug={dbg} pair={os.environ.get('PAIR', '0')} nacc={os.environ.get('DG_GEMM_NACC', '4')} B{B} H{H} {Cb}->{Cs} bn={bn}: down {md * 1e3:.1f} us {fl / md / 1e9:.0f} TF | "
               f"up {mu * 1e3:.1f} us {fl / mu / 1e9:.0f} TF")
     ops.set_conv_tiling(0, -1)

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name"; t0=$SECONDS; timeout -k 5 400 "$@" > gpurun_out/$name.log 2>&1; echo "exit $? after $((SECONDS-t0))s" | tee -a gpurun_out/$name.log; grep '^{' gpurun_out/$name.log | cut -c1-190; }
+timeout -k 5 300 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -3
+DG_BN_STREAM=0 run b512_bn0 python bench.py --image-size 512 --steps 12 --warmup 6 --no-cpu-baseline --no-roofline
+DG_BN_STREAM=1 run b512_bn1 python bench.py --image-size 512 --steps 12 --warmup 6 --no-cpu-baseline --no-roofline
+DG_BN_STREAM=0 run b64_bn0 python bench.py --steps 60 --warmup 9 --also-512 0 --no-roofline --no-cpu-baseline
+DG_BN_STREAM=1 run b64_bn1 python bench.py --steps 60 --warmup 9 --also-512 0 --no-roofline --no-cpu-baseline
+DG_BN_STREAM=1 DG_GEMM_PAIR=0 run b512_bn1_nopair python bench.py --image-size 512 --steps 12 --warmup 6 --no-cpu-baseline --no-roofline
+DG_BN_STREAM=1 DG_GEMM_PAIR=0 run b64_bn1_nopair python bench.py --steps 60 --warmup 9 --also-512 0 --no-roofline --no-cpu-baseline
