@@ -440,6 +440,206 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Role-swapped variant for layers with <= 128 output channels.  A tcgen05.mma costs ~130 cycles + 0.3 * N regardless
+// of N (measured: MMA-only rate 1450 / 830 / 510 TFLOP/s for N = 256 / 128 / 64), so a 128 x 64 tile can never run at
+// more than a third of the tensor peak.  Here the WEIGHTS are the M operand (M = Cout = 64 or 128 rows) and 256 PIXELS
+// (two consecutive 128-pixel tiles) are the N operand: every MMA is N = 256 wide.  The accumulator is D^T -- TMEM lane =
+// output channel, column = pixel -- so a thread owns one channel: BatchNorm partial sums are plain register sums, and
+// the 32 lanes of a warp store 32 consecutive channels (64 contiguous bytes) of one pixel per instruction.
+// M = 64: the accumulator occupies lanes 0-15 of each 32-lane TMEM quarter (16 data paths per warp).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSwapN = 256;
+constexpr int kSwapTrStride = 36;   // floats per row of the epilogue transpose tile (32 + 4 padding)
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_constant__ CUtensorMap tmW,
+                      const ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int w_bytes = p.N * 128;                       // weight tile: Cout rows x 64 k
+  const int stage_bytes = 2 * kATileBytes + w_bytes;   // 256 pixel rows + the weight rows
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.num_stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_units = p.num_tiles >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmPix);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  griddep_launch_dependents();
+  griddep_wait();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const TileCoord t0 = decode_tile(p, 2 * u), t1 = decode_tile(p, 2 * u + 1);   // same parity plane
+        const int py = t0.par >> 1, px = t0.par & 1;
+        for (int it = 0; it < p.k_iters; ++it) {
+          const int tap_i = it / p.cpk;
+          const int c0 = (it - tap_i * p.cpk) * kBlockK;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sp = smem + stage * stage_bytes;
+          uint8_t* sw = sp + 2 * kATileBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          if (p.mode == 0) {
+            const int kh = tap_i >> 2, kw = tap_i & 3;
+            const int dh = ((kh + 1) >> 1) - 1, ph = (kh + 1) & 1;
+            const int dw = ((kw + 1) >> 1) - 1, pw = (kw + 1) & 1;
+            tma_load_5d(sp, &tmPix, &full_bar[stage], pw * p.Ck + c0, t0.w0 + dw, ph, t0.h0 + dh, t0.b0);
+            tma_load_5d(sp + kATileBytes, &tmPix, &full_bar[stage], pw * p.Ck + c0, t1.w0 + dw, ph, t1.h0 + dh, t1.b0);
+            tma_load_2d(sw, &tmW, &full_bar[stage], tap_i * p.Ck + c0, 0);
+          } else {
+            const int th = tap_i >> 1, tw = tap_i & 1;
+            const int kh = py == 0 ? (th ? 3 : 1) : (th ? 2 : 0);
+            const int di = py == 0 ? (th ? -1 : 0) : (th ? 0 : 1);
+            const int kw = px == 0 ? (tw ? 3 : 1) : (tw ? 2 : 0);
+            const int dj = px == 0 ? (tw ? -1 : 0) : (tw ? 0 : 1);
+            tma_load_4d(sp, &tmPix, &full_bar[stage], c0, t0.w0 + dj, t0.h0 + di, t0.b0);
+            tma_load_4d(sp + kATileBytes, &tmPix, &full_bar[stage], c0, t1.w0 + dj, t1.h0 + di, t1.b0);
+            tma_load_2d(sw, &tmW, &full_bar[stage], (kh * 4 + kw) * p.Ck + c0, 0);
+          }
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(p.N, kSwapN, 0, 0);
+      const uint64_t desc_base = make_sdesc_sw128(0, 16, 1024);
+      const uint32_t smem0 = smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+        for (int it = 0; it < p.k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sp = smem0 + (uint32_t)(stage * stage_bytes);
+          const uint64_t dpix = desc_base | (uint64_t)((sp & 0x3FFFFu) >> 4);
+          const uint64_t dwt = desc_base | (uint64_t)(((sp + 2 * kATileBytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(d_tmem, dwt + (uint64_t)(2 * k), dpix + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const bool m64 = p.N == 64;
+    const int ch = m64 ? q * 16 + lane : q * 32 + lane;   // this thread's output channel
+    const bool ch_ok = !m64 || lane < 16;
+    const int lw = 31 - __clz(p.Wt), lh = 31 - __clz(p.Ht);   // tile extents are powers of two
+    // per-warp transpose tile [32 pixels][32 channels] fp32, rows padded to 144 bytes (conflict-free 16-byte reads)
+    float* tr = reinterpret_cast<float*>(smem + p.num_stages * stage_bytes + 1024) + (warp - 2) * 32 * kSwapTrStride;
+    float ssum = 0.f, ssq = 0.f;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const TileCoord tA = decode_tile(p, 2 * u), tB = decode_tile(p, 2 * u + 1);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
+      for (int c = 0; c < kSwapN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        // (1) this thread's channel, 32 pixels -> statistics in registers, values into the warp's transpose tile
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float v = __uint_as_float(r[e]);
+          ssum += v;            // rows beyond the batch are exact zeros (TMA zero fill)
+          ssq += v * v;
+          if (ch_ok) tr[e * kSwapTrStride + lane] = v;
+        }
+        __syncwarp();
+        // (2) this thread's pixel, the warp's 32 (16) channels -> 16-byte vector stores
+        const bool first = c < 128;
+        const int tb0 = first ? tA.b0 : tB.b0, th0 = first ? tA.h0 : tB.h0, tw0 = first ? tA.w0 : tB.w0;
+        const int row = (c & 127) + lane;
+        const int wl = row & (p.Wt - 1), hl = (row >> lw) & (p.Ht - 1), bl = row >> (lw + lh);
+        const int b = tb0 + bl;
+        int oy = th0 + hl, ox = tw0 + wl;
+        if (p.mode == 1) {
+          oy = 2 * oy + (tA.par >> 1);   // both tiles of a unit lie in the same parity plane
+          ox = 2 * ox + (tA.par & 1);
+        }
+        if (b < p.B) {
+          const size_t o = (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.N + (m64 ? q * 16 : q * 32);
+          const int nvec = m64 ? 2 : 4;
+          for (int j = 0; j < nvec; ++j) {
+            const float4 lo = *reinterpret_cast<const float4*>(tr + lane * kSwapTrStride + 8 * j);
+            const float4 hi = *reinterpret_cast<const float4*>(tr + lane * kSwapTrStride + 8 * j + 4);
+            float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            if (p.mask) {
+              float m[8];
+              unpack8(*reinterpret_cast<const bf16x8*>(p.mask + o + 8 * j), m);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] *= (m[k] > 0.f ? 1.f : p.mask_slope);
+            }
+            *reinterpret_cast<bf16x8*>(p.out + o + 8 * j) = pack8(f);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (p.stat_part && ch_ok) {
+      p.stat_part[(size_t)blockIdx.x * p.N + ch] = ssum;
+      p.stat_part[((size_t)gridDim.x + blockIdx.x) * p.N + ch] = ssq;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 // split-K finish: fp32 workspace -> bf16 output (8 elements per thread)
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const float* __restrict__ ws, bf16* __restrict__ out, long long n8) {
@@ -744,7 +944,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 float* g_splitk_ws = nullptr;
 size_t g_splitk_ws_bytes = 0;
 // test hooks (dg_conv_set_tiling): force the N tile (0 = heuristic) and switch CTA pairs (-1 = default / DG_GEMM_PAIR)
-int g_force_bn = 0;
+int g_force_bn = 0;      // 1 = force the role-swapped kernel wherever it is eligible
 int g_force_pair = -1;
 
 struct ConvGemmExtras {
@@ -818,7 +1018,18 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   if (!img_mode && !ex.mask && g_splitk_ws && gflop_all > 16.0 && k_iters_all >= 64 && N % 256 == 0 &&
       (long long)m_tiles * (N / 256) * 2 <= num_sms())
     bn = 256;
-  if (g_force_bn && !img_mode && N % g_force_bn == 0) bn = g_force_bn;
+  if (g_force_bn > 1 && !img_mode && N % g_force_bn == 0) bn = g_force_bn;
+  // narrow layers (<= 128 output channels): role-swapped kernel, weights as M, 256 pixels as N
+  static int swap_mode = -1;
+  if (swap_mode < 0) {
+    const char* e = getenv("DG_GEMM_SWAP");
+    swap_mode = e ? atoi(e) : 1;
+  }
+  const int tiles_plane = p.tiles_w * p.tiles_h * p.tiles_b;
+  const bool swap_ok = !img_mode && (N == 64 || N == 128) && tiles_plane % 2 == 0;
+  const bool use_swap = swap_ok && g_force_bn != 64 && g_force_bn != 128 &&
+                        (g_force_bn == 1 || (swap_mode && m_tiles / 2 >= (num_sms() * 7) / 8));
+  if (use_swap) bn = N;
   p.block_n = bn;
   p.n_tiles = N / bn;
   p.num_tiles = m_tiles * p.n_tiles;
@@ -851,7 +1062,7 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   while (!img_mode && p.nacc * 2 <= nacc_mode && p.nacc * 2 * bn <= kAccStride) p.nacc *= 2;
   const double gflop = 2.0 * B * Hs * Ws * (double)Cs * Cb * 16 * 1e-9;
   const size_t ws_need = (size_t)B * p.Ho * p.Wo * N * sizeof(float);
-  if (!img_mode && !ex.mask && g_splitk_ws && ws_need <= g_splitk_ws_bytes && gflop > 16.0 &&
+  if (!use_swap && !img_mode && !ex.mask && g_splitk_ws && ws_need <= g_splitk_ws_bytes && gflop > 16.0 &&
       p.num_tiles * 2 <= num_sms() && p.k_iters >= 64) {
     int splits = num_sms() / p.num_tiles;
     if (splits > p.k_iters / 32) splits = p.k_iters / 32;
@@ -870,8 +1081,9 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   }
   const int tiles_per_plane = p.tiles_w * p.tiles_h * p.tiles_b;
   const int want_pair = g_force_pair >= 0 ? g_force_pair : pair_mode;
-  const int ncta = (want_pair && !img_mode && bn >= 64 && tiles_per_plane % 2 == 0) ? 2 : 1;
-  const int work = (p.num_tiles / ncta) * p.splits;
+  const int ncta = (!use_swap && want_pair && !img_mode && bn >= 64 && tiles_per_plane % 2 == 0) ? 2 : 1;
+  int work = (p.num_tiles / ncta) * p.splits;
+  if (use_swap) work = p.num_tiles / 2;
   const int max_units = num_sms() / ncta;
   const int grid = (work < max_units ? work : max_units) * ncta;
   if (ex.grid_out) {
@@ -882,11 +1094,12 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     DG_CHECK_ARG(ex.stat_part == nullptr, "conv gemm: fused statistics requested for a split-K shape");
     cudaMemsetAsync(p.ws, 0, ws_need, stream);
   }
-  const int stage_bytes = kATileBytes + (bn / ncta) * 128;
+  const int stage_bytes = use_swap ? 2 * kATileBytes + N * 128 : kATileBytes + (bn / ncta) * 128;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
-  const int smem_bytes = stages * stage_bytes + 1024 + 256 + (ex.stat_part ? 2 * N * (int)sizeof(float) : 0);
+  const int smem_bytes = stages * stage_bytes + 1024 + 256 + (ex.stat_part && !use_swap ? 2 * N * (int)sizeof(float) : 0) +
+                         (use_swap ? 4 * 32 * kSwapTrStride * 4 + 768 : 0);
   DG_CHECK_ARG(smem_bytes <= 227 * 1024, "conv gemm: N=%d too wide for fused statistics", N);
 
   CUtensorMap tmA, tmB;
@@ -894,11 +1107,11 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   if (mode == 0) {
     rc = make_parity_map(&tmA, a, B, 2 * Hs, 2 * Ws, Cb, p.Wt, p.Ht, p.Bt);
     if (rc) return rc;
-    rc = make_weight_map(&tmB, wpacked, Cs, 16 * Cb, bn / ncta);
+    rc = make_weight_map(&tmB, wpacked, Cs, 16 * Cb, use_swap ? N : bn / ncta);
   } else {
     rc = make_nhwc_map(&tmA, a, B, Hs, Ws, Cs, p.Wt, p.Ht, p.Bt);
     if (rc) return rc;
-    rc = make_weight_map(&tmB, wpacked, Cb, 16 * Cs, bn / ncta);
+    rc = make_weight_map(&tmB, wpacked, Cb, 16 * Cs, use_swap ? N : bn / ncta);
   }
   if (rc) return rc;
   static bool attr_set = false;
@@ -906,13 +1119,17 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gemm_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       dg_set_error("conv gemm: cannot raise dynamic smem: %s", cudaGetErrorString(e));
       return DG_ERR_CUDA;
     }
     attr_set = true;
   }
-  if (ncta == 2)
+  if (use_swap)
+    dg_launch(conv_gemm_swap_kernel, dg_cfg(grid, kThreads, smem_bytes, stream), tmA, tmB, p);
+  else if (ncta == 2)
     dg_launch(conv_gemm_kernel<2>, dg_cfg(grid, kThreads, smem_bytes, stream, 2), tmA, tmB, p);
   else
     dg_launch(conv_gemm_kernel<1>, dg_cfg(grid, kThreads, smem_bytes, stream), tmA, tmB, p);
@@ -969,7 +1186,8 @@ int dg_conv4x4s2_dgrad(const void* dz, const void* wu, void* dx, int B, int Hs, 
 // Register a device workspace for split-K (fp32 [output pixels][N] of the largest split layer; 64 MB covers the
 // 512x512 family).  NULL/0 disables split-K.  The buffer is used by launches on any stream in program order.
 int dg_conv_set_tiling(int block_n, int pair) {
-  DG_CHECK_ARG(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 256, "conv tiling: block_n=%d", block_n);
+  DG_CHECK_ARG(block_n == 0 || block_n == 1 || block_n == 64 || block_n == 128 || block_n == 256,
+               "conv tiling: block_n=%d", block_n);
   g_force_bn = block_n;
   g_force_pair = pair;
   return DG_OK;

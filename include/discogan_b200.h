@@ -52,7 +52,8 @@ int dg_conv4x4s2_dgrad(const void* dz_small, const void* wu, void* dx_big, int B
                        dg_stream_t stream);
 /* device workspace for split-K of the small-M / large-K layers (fp32 [output pixels][N]); NULL disables split-K */
 int dg_conv_set_splitk_workspace(void* ws, size_t bytes);
-/* test hook: force the GEMM N tile (64/128/256, 0 = heuristic) and the use of CTA pairs -- tcgen05 cta_group::2, two
+/* test hook: force the GEMM N tile (64/128/256, 0 = heuristic, 1 = the role-swapped kernel for <= 128 output
+ * channels wherever it is eligible) and the use of CTA pairs -- tcgen05 cta_group::2, two
  * M tiles per MMA -- (1/0, -1 = default: on, env DG_GEMM_PAIR=0 turns it off).  Results do not depend on either. */
 int dg_conv_set_tiling(int block_n, int pair);
 /* forward convolutions with the BatchNorm statistics of the output fused in the epilogue: stat_part = float[2*rows*N]

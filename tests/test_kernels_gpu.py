@@ -473,3 +473,41 @@ def test_conv_cta_pairs(bn, B, H, Cb, Cs):
     stu = ops.bn_stats_finalize(partu, Pu, gu, bu)
     refu = ops.bn_stats(zu.view(Pu, Cb), gu, bu)
     assert torch.allclose(stu[0], refu[0], atol=3e-3, rtol=1e-2) and torch.allclose(stu[1], refu[1], rtol=1e-2)
+
+
+@pytest.mark.parametrize("B,H,Cb,Cs", [(4, 16, 64, 128),      # DOWN: 128 output channels; UP: 64 (M = 64 accumulator)
+                                       (3, 32, 64, 128),      # tiles of half an image, odd batch
+                                       (11, 16, 128, 256),    # UP: 128 output channels, batch remainder in the last tile
+                                       (1, 256, 64, 128)])    # the 512^2 geometry: one image row per tile
+def test_conv_role_swapped(B, H, Cb, Cs):
+    """Layers with <= 128 output channels run with the weights as the MMA M operand and 256 pixels as N (transposed
+    accumulator): same results as the regular kernel, incl. fused statistics and the masked dgrad epilogue."""
+    ops = ops_mod()
+    x = rnd(B, Cb, H, H, seed=1).to(BF16)
+    w = (rnd(Cs, Cb, 4, 4, seed=2) / (4 * Cb ** 0.5)).to(BF16).float()
+    wd, wu = ops.pack_weights(w)
+    xn = to_nhwc_bf16(x.float())
+    s = rnd(B, Cs, H // 2, H // 2, seed=3).to(BF16)
+    sn = to_nhwc_bf16(s.float())
+    mask = to_nhwc_bf16(rnd(B, Cb, H, H, seed=4))
+    ref_d = F.conv2d(x.float(), w, stride=2, padding=1)
+    ref_u = F.conv_transpose2d(s.float(), w, stride=2, padding=1)
+    try:
+        ops.set_conv_tiling(64, 0)
+        d1, u1, um1 = ops.conv_down(xn, wd), ops.conv_up(sn, wu), ops.conv_up(sn, wu, mask=mask, slope=0.2)
+        ops.set_conv_tiling(1, 0)
+        d2, u2, um2 = ops.conv_down(xn, wd), ops.conv_up(sn, wu), ops.conv_up(sn, wu, mask=mask, slope=0.2)
+        z, part = ops.conv_down_stats(xn, wd)
+        zu, partu = ops.conv_up_stats(sn, wu)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_conv_tiling(0, -1)
+    assert rel_l2(to_nchw_f32(d2), ref_d) < 4e-3 and rel_l2(to_nchw_f32(u2), ref_u) < 4e-3
+    assert torch.equal(d1, d2) and torch.equal(u1, u2) and torch.equal(um1, um2)   # same K order, fp32 accumulation
+    assert torch.equal(z, d2) and torch.equal(zu, u2)
+    for zz, pp, C in ((z, part, Cs), (zu, partu, Cb)):
+        P = zz.numel() // C
+        g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+        st = ops.bn_stats_finalize(pp, P, g, b)
+        ref = ops.bn_stats(zz.view(P, C), g, b)
+        assert torch.allclose(st[0], ref[0], atol=3e-3, rtol=1e-2) and torch.allclose(st[1], ref[1], rtol=1e-2)
