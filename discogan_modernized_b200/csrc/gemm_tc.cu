@@ -1013,9 +1013,21 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   }
   // SM-starved big GEMMs (few M tiles, long K): prefer the widest N tile (best bytes/FLOP) and fill the machine with
   // split-K instead of shrinking the tile
+  // split-K thresholds: minimum problem size and minimum k-iterations per split.  Measured on the 64^2 step
+  // (B = 64): 1 GFLOP / 16 k-iterations gives 2.04 ms/step against 2.16 without split-K on the 4-GFLOP deep layers;
+  // 8 k-iterations per split loses it again to the reduction traffic
+  static double sk_gflop = -1.0;
+  static int sk_mink = 16;
+  if (sk_gflop < 0.0) {
+    const char* e = getenv("DG_SPLITK_GFLOP");
+    sk_gflop = e ? atof(e) : 1.0;
+    const char* e2 = getenv("DG_SPLITK_MINK");
+    sk_mink = e2 ? atoi(e2) : 16;
+    if (sk_mink < 1) sk_mink = 1;
+  }
   const double gflop_all = 2.0 * B * Hs * Ws * (double)Cs * Cb * 16 * 1e-9;
   const int k_iters_all = (mode == 0 ? 16 : 4) * ((mode == 0 ? Cb : Cs) / 64);
-  if (!img_mode && !ex.mask && g_splitk_ws && gflop_all > 16.0 && k_iters_all >= 64 && N % 256 == 0 &&
+  if (!img_mode && !ex.mask && g_splitk_ws && gflop_all > sk_gflop && k_iters_all >= 2 * sk_mink && N % 256 == 0 &&
       (long long)m_tiles * (N / 256) * 2 <= num_sms())
     bn = 256;
   if (g_force_bn > 1 && !img_mode && N % g_force_bn == 0) bn = g_force_bn;
@@ -1062,10 +1074,10 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   while (!img_mode && p.nacc * 2 <= nacc_mode && p.nacc * 2 * bn <= kAccStride) p.nacc *= 2;
   const double gflop = 2.0 * B * Hs * Ws * (double)Cs * Cb * 16 * 1e-9;
   const size_t ws_need = (size_t)B * p.Ho * p.Wo * N * sizeof(float);
-  if (!use_swap && !img_mode && !ex.mask && g_splitk_ws && ws_need <= g_splitk_ws_bytes && gflop > 16.0 &&
-      p.num_tiles * 2 <= num_sms() && p.k_iters >= 64) {
+  if (!use_swap && !img_mode && !ex.mask && g_splitk_ws && ws_need <= g_splitk_ws_bytes && gflop > sk_gflop &&
+      p.num_tiles * 2 <= num_sms() && p.k_iters >= 2 * sk_mink) {
     int splits = num_sms() / p.num_tiles;
-    if (splits > p.k_iters / 32) splits = p.k_iters / 32;
+    if (splits > p.k_iters / sk_mink) splits = p.k_iters / sk_mink;
     if (splits > 1) {
       p.kps = dg_ceil_div(p.k_iters, splits);
       p.splits = dg_ceil_div(p.k_iters, p.kps);
