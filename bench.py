@@ -26,8 +26,8 @@ sys.path.insert(0, str(ROOT))
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--image-size", type=int, default=64)
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default 64 at 64^2, 32 at 512^2)")
@@ -65,11 +65,18 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.monotonic()
+
+    def mark_end(self):
+        self.t1 = time.monotonic()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -78,7 +85,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -90,7 +97,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        # the sampler runs from before the warm-up; only samples that arrived inside the marked window (the timed
+        # steps and the host-fed timed steps that follow them) are reported
+        lines = [ln for t, ln in self.lines if self.t0 is None or (self.t0 <= t <= (self.t1 or t))]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -360,14 +370,15 @@ def measure_roofline(tr, batches, torch, pk):
         if 3 * g[1] < 0.02:      # a burst of a few milliseconds: compare with the burst figure
             peak, peak_src = pk["tf_burst"], f"{pk['src']} bf16 burst (kernel timed alone, {3 * g[1] * 1e3:.0f} ms of launches)"
     ach = g[0] / g[1] / 1e12
-    # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel (profiles/README.md); only the
-    # 512^2 B=32 workload has been captured so far
+    # DRAM traffic per launch from the committed `ncu --set full` captures of this kernel (profiles/README.md)
     traffic = None
     tfile = ROOT / "profiles" / "ncu_traffic.json"
     big = batches[0][0]
-    if tfile.exists() and big.shape[-1] == 512 and big.shape[0] == 32:
-        traffic = json.loads(tfile.read_text())["conv_gemm_kernel"]["dram_bytes_per_launch"]
-    roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM: conv fprop/dgrad, convT fprop/dgrad)",
+    if tfile.exists():
+        key = {(512, 32): "conv_gemm_kernel", (64, 64): "conv_gemm_kernel_64x64_b64"}.get((big.shape[-1], big.shape[0]))
+        ent = json.loads(tfile.read_text()).get(key) if key else None
+        traffic = ent["dram_bytes_per_launch"] if ent else None
+    roof = {"bound": "tensor", "kernel": "conv_gemm_kernel<1|2> + conv_gemm_swap_kernel (tcgen05 implicit GEMM: conv fprop/dgrad, convT fprop/dgrad)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "peak_source": peak_src, "traffic": traffic,
             "launches_per_cycle": g[2], "avg_launch_us": g[1] / max(g[2], 1) * 1e6,
@@ -395,18 +406,20 @@ def run_b200(args, S, B):
     tr = DiscoGANTrainer(image_size=S, device=f"cuda:{local}", model_arch=args.model_arch, seed=1234)
     host = [tuple(t.pin_memory() for t in synthetic_batch(B, S, step=i, rank=rank)) for i in range(3)]
     batches = [(a.cuda(non_blocking=True), b.cuda(non_blocking=True)) for a, b in host]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                         # nvidia-smi needs ~0.1 s to deliver its first sample: start it early
     for i in range(warmup):
         tr.step(*batches[i % 3])
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     L0 = tr.kernel_launches
+    sampler.mark_begin()
     ms = timed_steps(tr, batches, steps, torch, dist, world)
     launches = tr.kernel_launches - L0          # kernels of libdiscogan_b200.so (eager launches + graph-replayed nodes)
-    clocks = sampler.stop() if rank == 0 else None
     ms_e2e, h2d, d2h = timed_steps_e2e(tr, host, steps, torch, dist, world)
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     pairs = B * world * steps
     value = pairs / (ms * 1e-3)
     pk = peaks()
