@@ -428,7 +428,7 @@ def run_b200(args, S, B):
         "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(S, B), "image_size": S, "batch_per_gpu": B, "global_batch": B * world,
-                   "model_arch": args.model_arch, "parallelism": f"dp{world}", "cuda_graphs": bool(tr.use_graphs), "lanes": 2 if tr._side is not None else 1,
+                   "model_arch": args.model_arch, "parallelism": f"dp{world}", "cuda_graphs": bool(tr.use_graphs), "lanes": 1 + (1 + len(tr._more) if tr._side is not None else 0),
                    "l2": "per-step working set (weights+grads+Adam moments+activations) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "image-pairs/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / steps},
