@@ -61,7 +61,8 @@ struct ConvGemmParams {
                       // short to hide; the k-substeps of a stage round-robin over nacc column blocks that the
                       // epilogue sums
   int debug;          // timing experiments (env DG_GEMM_DEBUG, results are garbage): 1 = no MMAs, 2 = no A loads,
-                      // 3 = no B loads, 4 = no loads at all, 5 = no loads and A operand from TMEM
+                      // 3 = no B loads, 4 = no loads at all, 5 = no loads and A operand from TMEM,
+                      // 6 = role-swapped kernel without the mask prefetch (results stay correct)
 };
 
 // Sum the 32 values each lane holds for 32 columns over the 32 lanes (rows) of the warp: afterwards v[0] of lane l is
@@ -575,10 +576,51 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       const TileCoord tA = decode_tile(p, 2 * u), tB = decode_tile(p, 2 * u + 1);
+      // element offset of (this lane's pixel of chunk c, this warp's first channel); -1 beyond the batch
+      auto row_offset = [&](int c) -> long long {
+        const bool first = c < 128;
+        const int row = (c & 127) + lane;
+        const int wl = row & (p.Wt - 1), hl = (row >> lw) & (p.Ht - 1), bl = row >> (lw + lh);
+        const int b = (first ? tA.b0 : tB.b0) + bl;
+        int oy = (first ? tA.h0 : tB.h0) + hl, ox = (first ? tA.w0 : tB.w0) + wl;
+        if (p.mode == 1) {
+          oy = 2 * oy + (tA.par >> 1);   // both tiles of a unit lie in the same parity plane
+          ox = 2 * ox + (tA.par & 1);
+        }
+        if (b >= p.B) return -1;
+        return (long long)((((size_t)b * p.Ho + oy) * p.Wo + ox) * p.N + (m64 ? q * 16 : q * 32));
+      };
+      const int nvec = m64 ? 2 : 4;
+      // masked dgrad: the mask rows are fetched ahead of their use -- L2 prefetch of all eight chunk rows while the
+      // unit's MMAs are still running, and the 16-byte vectors of chunk c+1 are loaded while chunk c is processed
+      uint4 mcur[4], mnext[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mcur[j] = mnext[j] = make_uint4(0u, 0u, 0u, 0u);
+      const bool pre = p.mask != nullptr && p.debug != 6;
+      if (pre) {
+        for (int c = 0; c < kSwapN; c += 32) {
+          const long long o = row_offset(c);
+          if (o >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask + o));
+        }
+        const long long o0 = row_offset(0);
+        if (o0 >= 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nvec) mcur[j] = *reinterpret_cast<const uint4*>(p.mask + o0 + 8 * j);
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
       for (int c = 0; c < kSwapN; c += 32) {
+        if (pre && c + 32 < kSwapN) {
+          const long long on = row_offset(c + 32);
+          if (on >= 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < nvec) mnext[j] = *reinterpret_cast<const uint4*>(p.mask + on + 8 * j);
+          }
+        }
         uint32_t r[32];
         tmem_ld_32x32(taddr + c, r);
         tmem_ld_wait();
@@ -592,32 +634,27 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
         }
         __syncwarp();
         // (2) this thread's pixel, the warp's 32 (16) channels -> 16-byte vector stores
-        const bool first = c < 128;
-        const int tb0 = first ? tA.b0 : tB.b0, th0 = first ? tA.h0 : tB.h0, tw0 = first ? tA.w0 : tB.w0;
-        const int row = (c & 127) + lane;
-        const int wl = row & (p.Wt - 1), hl = (row >> lw) & (p.Ht - 1), bl = row >> (lw + lh);
-        const int b = tb0 + bl;
-        int oy = th0 + hl, ox = tw0 + wl;
-        if (p.mode == 1) {
-          oy = 2 * oy + (tA.par >> 1);   // both tiles of a unit lie in the same parity plane
-          ox = 2 * ox + (tA.par & 1);
-        }
-        if (b < p.B) {
-          const size_t o = (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.N + (m64 ? q * 16 : q * 32);
-          const int nvec = m64 ? 2 : 4;
-          for (int j = 0; j < nvec; ++j) {
-            const float4 lo = *reinterpret_cast<const float4*>(tr + lane * kSwapTrStride + 8 * j);
-            const float4 hi = *reinterpret_cast<const float4*>(tr + lane * kSwapTrStride + 8 * j + 4);
-            float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            if (p.mask) {
-              float m[8];
-              unpack8(*reinterpret_cast<const bf16x8*>(p.mask + o + 8 * j), m);
+        const long long o = row_offset(c);
+        if (o >= 0) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) f[k] *= (m[k] > 0.f ? 1.f : p.mask_slope);
+          for (int j = 0; j < 4; ++j) {
+            if (j < nvec) {
+              const float4 lo = *reinterpret_cast<const float4*>(tr + lane * kSwapTrStride + 8 * j);
+              const float4 hi = *reinterpret_cast<const float4*>(tr + lane * kSwapTrStride + 8 * j + 4);
+              float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+              if (p.mask) {
+                float m[8];
+                const bf16x8 mv = pre ? mcur[j] : *reinterpret_cast<const bf16x8*>(p.mask + o + 8 * j);
+                unpack8(mv, m);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] *= (m[k] > 0.f ? 1.f : p.mask_slope);
+              }
+              *reinterpret_cast<bf16x8*>(p.out + o + 8 * j) = pack8(f);
             }
-            *reinterpret_cast<bf16x8*>(p.out + o + 8 * j) = pack8(f);
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mcur[j] = mnext[j];
         __syncwarp();
       }
       tc_fence_before();

@@ -31,6 +31,7 @@ for (B, H, Cb, Cs) in [(32, 256, 64, 128), (32, 128, 128, 256), (64, 32, 64, 128
         ops.set_conv_tiling(bn, -1)
         md = timeit(lambda: ops.conv_down(big, wd))
         mu = timeit(lambda: ops.conv_up(small, wu))
+        mm = timeit(lambda: ops.conv_up(small, wu, mask=big, slope=0.2))
         print(f"{name} B{B} H{H} {Cb}->{Cs}: down {md * 1e3:.1f} us {fl / md / 1e9:.0f} TF | "
-              f"up {mu * 1e3:.1f} us {fl / mu / 1e9:.0f} TF")
+              f"up {mu * 1e3:.1f} us {fl / mu / 1e9:.0f} TF | masked up {mm * 1e3:.1f} us {fl / mm / 1e9:.0f} TF")
     ops.set_conv_tiling(0, -1)
