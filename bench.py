@@ -149,7 +149,7 @@ def run_reference(args, S, B):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(3, args.steps // 3 * 3)
+    steps = max(1, args.steps)                 # exactly K steps (the D:G:G schedule simply continues across them)
     v, ms, cores, sample, Bs = cpu_reference_pairs_per_s(S, B, steps, max(1, args.warmup), args.model_arch)
     line = {
         "impl": "reference", "metric": "train image-pairs/sec", "value": v, "unit": "image-pairs/s", "n_gpus": args.gpus,
@@ -401,7 +401,7 @@ def run_b200(args, S, B):
     from discogan_modernized_b200 import DiscoGANTrainer, _lib
     from oracle.step import synthetic_batch           # seeded synthetic inputs only (no oracle compute on this arm)
 
-    steps = max(3, args.steps // 3 * 3)
+    steps = max(1, args.steps)                 # exactly K timed steps; the D:G:G schedule simply continues across them
     warmup = max(3, args.warmup)
     tr = DiscoGANTrainer(image_size=S, device=f"cuda:{local}", model_arch=args.model_arch, seed=1234)
     host = [tuple(t.pin_memory() for t in synthetic_batch(B, S, step=i, rank=rank)) for i in range(3)]
