@@ -399,7 +399,14 @@ def run_b200(args, S, B):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     from discogan_modernized_b200 import DiscoGANTrainer, _lib
-    from oracle.step import synthetic_batch           # seeded synthetic inputs only (no oracle compute on this arm)
+
+    def synthetic_batch(batch, image_size, step=0, rank=0, device="cpu"):
+        """A, B = uniform [0,1) fp32 images from seed 1000*rank+step; same recipe as the oracle's
+        helper, restated here so that nothing under oracle/ is imported on this arm."""
+        g = torch.Generator().manual_seed(1000 * rank + step)
+        A = torch.rand(batch, 3, image_size, image_size, generator=g)
+        Bt = torch.rand(batch, 3, image_size, image_size, generator=g)
+        return A.to(device), Bt.to(device)
 
     steps = max(1, args.steps)                 # exactly K timed steps; the D:G:G schedule simply continues across them
     warmup = max(3, args.warmup)

@@ -54,3 +54,20 @@ def test_clock_sampler_window():
     c = s.stop()
     assert c["samples"] == 2 and c["sm_mhz"] in (1900.0, 1950.0) and c["sm_max_mhz"] == 1965.0
     assert c["reasons"] == ["sw_power_cap"]
+
+
+def test_product_and_b200_arm_never_import_the_oracle():
+    """oracle/ is test infrastructure: only tests/, smoke() and the CPU legs of bench.py may touch it."""
+    import ast
+    tree = ast.parse((ROOT / "bench.py").read_text())
+    allowed = {"cpu_reference_pairs_per_s"}                      # cpu_baseline leg and --impl reference
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        mods = [n.module for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and n.module] + \
+               [a.name for n in ast.walk(fn) if isinstance(n, ast.Import) for a in n.names]
+        if any(m.split(".")[0] == "oracle" for m in mods):
+            assert fn.name in allowed, f"bench.py:{fn.name} imports oracle"
+    for py in (ROOT / "discogan_modernized_b200").glob("*.py"):
+        t = ast.parse(py.read_text())
+        mods = [n.module for n in ast.walk(t) if isinstance(n, ast.ImportFrom) and n.module] + \
+               [a.name for n in ast.walk(t) if isinstance(n, ast.Import) for a in n.names]
+        assert not any(m.split(".")[0] == "oracle" for m in mods), f"{py.name} imports oracle"
