@@ -409,7 +409,8 @@ def run_b200(args, S, B):
         return A.to(device), Bt.to(device)
 
     steps = max(1, args.steps)                 # exactly K timed steps; the D:G:G schedule simply continues across them
-    warmup = max(3, args.warmup)
+    warmup = max(6, args.warmup)               # at least two D:G:G cycles: the first captures the step graphs, the second
+                                               # replays each of them once (first-replay upload) outside the timed region
     tr = DiscoGANTrainer(image_size=S, device=f"cuda:{local}", model_arch=args.model_arch, seed=1234)
     host = [tuple(t.pin_memory() for t in synthetic_batch(B, S, step=i, rank=rank)) for i in range(3)]
     batches = [(a.cuda(non_blocking=True), b.cuda(non_blocking=True)) for a, b in host]
