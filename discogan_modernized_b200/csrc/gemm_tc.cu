@@ -937,6 +937,181 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (DG_WGRAD_PAIR=1, off by default; written at the end of round 1, NOT yet run on hardware): the wgrad GEMM
+// as CTA pairs.  Two CTAs (m-tiles 2mp, 2mp+1 of one n-tile / tap half / split) issue M = 256 tcgen05.mma.cta_group::2:
+// each CTA loads its own 128 cs rows of `small` and only FOUR of the eight tap boxes of `big` -- the N = 256 operand of
+// MMA group g (taps 4g..4g+3) is split across the pair, CTA r supplying taps 4g+2r, 4g+2r+1 -- so an SM ingests 24 KB
+// per 32-pixel chunk instead of 40 KB (the existing cluster mode multicasts the boxes: same L2 reads, but every SM still
+// receives all 40 KB).  Accumulator layout, epilogue, workspace and reduce kernel are those of wgrad_gemm_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWpStageBytes = 6 * kWgBoxBytes;   // 2 boxes of `small` + 4 tap boxes of `big`
+constexpr int kWpStages = 8;                     // 8 x 24 KB
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmBig,
+                       const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWpStages * kWpStageBytes);
+  uint64_t* full_bar = bars;                 // used in the leader CTA only
+  uint64_t* empty_bar = bars + kWpStages;
+  uint64_t* tfull_bar = bars + 2 * kWpStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  int v = blockIdx.x >> 1;
+  const int mp = v % (p.m_tiles >> 1);
+  v /= (p.m_tiles >> 1);
+  const int half = v & 1;
+  const int nt = v >> 1;
+  const int mt = 2 * mp + (int)crank;
+  const int split = blockIdx.y;
+  const int chunk_begin = split * p.chunks_per_split;
+  const int chunk_end = min(p.total_chunks, chunk_begin + p.chunks_per_split);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmS);
+    tma_prefetch_desc(&tmBig);
+    for (int s = 0; s < kWpStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();
+  griddep_launch_dependents();
+  griddep_wait();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ch = chunk_begin; ch < chunk_end; ++ch) {
+        int r = ch;
+        const int cw = r % p.chunks_w;
+        r /= p.chunks_w;
+        const int chh = r % p.chunks_h;
+        const int cb_ = r / p.chunks_h;
+        const int w0 = cw * p.Wt, h0 = chh * p.Ht, b0 = cb_ * p.Bt;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * kWpStageBytes;
+        uint8_t* sb = sa + 2 * kWgBoxBytes;
+        if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 * kWpStageBytes));   // both CTAs' bytes
+        tma_load_4d_2cta(sa, &tmS, &full_bar[stage], mt * 128, w0, h0, b0);
+        tma_load_4d_2cta(sa + kWgBoxBytes, &tmS, &full_bar[stage], mt * 128 + 64, w0, h0, b0);
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) {
+          const int t = (t4 >> 1) * 4 + (int)crank * 2 + (t4 & 1);   // this CTA's share of MMA group t4 >> 1
+          const int tap = half * 8 + t;
+          const int kh = tap >> 2, kw = tap & 3;
+          const int dh = ((kh + 1) >> 1) - 1, ph = (kh + 1) & 1;
+          const int dw = ((kw + 1) >> 1) - 1, pw = (kw + 1) & 1;
+          tma_load_5d_2cta(sb + t4 * kWgBoxBytes, &tmBig, &full_bar[stage], pw * p.Cb + nt * 64, w0 + dw, ph, h0 + dh, b0);
+        }
+        if (++stage == kWpStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, 256, 1, 1);
+      const uint64_t desc_base = make_sdesc_sw128(0, kWgBoxBytes, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ch = chunk_begin; ch < chunk_end; ++ch) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kWpStageBytes);
+        const uint32_t sb = sa + 2 * kWgBoxBytes;
+#pragma unroll
+        for (int ks = 0; ks < kWgKC / 16; ++ks) {
+          const uint32_t accum = (ch > chunk_begin || ks > 0) ? 1u : 0u;
+          const uint64_t da = desc_base | (uint64_t)(((sa + ks * 2048) & 0x3FFFFu) >> 4);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t addr = sb + (uint32_t)(g * 2 * kWgBoxBytes) + ks * 2048u;
+            umma_bf16_2cta(tmem_base + (uint32_t)(g * 256), da, desc_base | (uint64_t)((addr & 0x3FFFFu) >> 4), idesc, accum);
+          }
+        }
+        umma_commit_2cta(&empty_bar[stage], 3);
+        if (++stage == kWpStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit_2cta(tfull_bar, 3);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (p.direct) {
+      float* drow = p.dw + (((size_t)(mt * 128 + row)) * p.Cb + (size_t)nt * 64) * 16 + half * 8;
+      for (int c8 = 0; c8 < 64; c8 += 8) {
+        uint32_t r[8][8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) tmem_ld_32x8(taddr + (uint32_t)(t * 64 + c8), r[t]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float* d = drow + (size_t)(c8 + j) * 16;
+          float4 o0 = make_float4(__uint_as_float(r[0][j]), __uint_as_float(r[1][j]), __uint_as_float(r[2][j]),
+                                  __uint_as_float(r[3][j]));
+          float4 o1 = make_float4(__uint_as_float(r[4][j]), __uint_as_float(r[5][j]), __uint_as_float(r[6][j]),
+                                  __uint_as_float(r[7][j]));
+          if (p.beta == 1.f) {
+            red_add_f32x4(d, o0.x, o0.y, o0.z, o0.w);
+            red_add_f32x4(d + 4, o1.x, o1.y, o1.z, o1.w);
+            continue;
+          }
+          if (p.beta != 0.f) {
+            const float4 a0 = *reinterpret_cast<const float4*>(d);
+            const float4 a1 = *reinterpret_cast<const float4*>(d + 4);
+            o0.x += p.beta * a0.x; o0.y += p.beta * a0.y; o0.z += p.beta * a0.z; o0.w += p.beta * a0.w;
+            o1.x += p.beta * a1.x; o1.y += p.beta * a1.y; o1.z += p.beta * a1.z; o1.w += p.beta * a1.w;
+          }
+          *reinterpret_cast<float4*>(d) = o0;
+          *reinterpret_cast<float4*>(d + 4) = o1;
+        }
+      }
+    } else {
+      float* dst = p.ws + ((((size_t)split * p.m_tiles + mt) * p.n_tiles + nt) * 2 + half) * (size_t)(128 * 512) +
+                   (size_t)row * 512;
+      for (int c = 0; c < 512; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 vv = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          *reinterpret_cast<uint4*>(dst + c + 4 * j) = vv;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
+  }
+}
+
 // dw[cs][cb][tap] = beta*dw + sum_split ws[...]; one thread per (cs, cb, half) writes 8 consecutive taps.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float beta, int Cs, int Cb,
                                     int m_tiles, int n_tiles, int splits) {
@@ -1354,7 +1529,25 @@ int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta
     cluster_mode = e ? atoi(e) : 1;
   }
   p.cluster = (cluster_mode && !p.share && p.m_tiles % 2 == 0) ? 1 : 0;
-  dg_launch(wgrad_gemm_kernel, dg_cfg(grid, kThreads, smem_bytes, stream, p.cluster ? 2 : 1), tmS, tmBig, tmBig33, p);
+  static int pair_mode = -1;   // experimental cta_group::2 variant, see wgrad_gemm_pair_kernel
+  if (pair_mode < 0) {
+    const char* e = getenv("DG_WGRAD_PAIR");
+    pair_mode = e ? atoi(e) : 0;
+  }
+  if (pair_mode && p.cluster && !p.debug) {
+    static bool pair_attr_set = false;
+    if (!pair_attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) {
+        dg_set_error("wgrad: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+        return DG_ERR_CUDA;
+      }
+      pair_attr_set = true;
+    }
+    dg_launch(wgrad_gemm_pair_kernel, dg_cfg(grid, kThreads, kWpStages * kWpStageBytes + 1024 + 256, stream, 2), tmS, tmBig, p);
+  } else {
+    dg_launch(wgrad_gemm_kernel, dg_cfg(grid, kThreads, smem_bytes, stream, p.cluster ? 2 : 1), tmS, tmBig, tmBig33, p);
+  }
   DG_CHECK_LAUNCH("wgrad_gemm_kernel");
   if (p.direct) return DG_OK;
   const long long total = (long long)Cs * Cb * 2;
