@@ -54,3 +54,26 @@ def test_ops_refuse_cpu_tensors():
         ops._ptr(torch.zeros(4), torch.float32, "x")
     with pytest.raises(ValueError):
         ops._ptr(torch.zeros(4, dtype=torch.float64), None, "x").__class__  # cpu tensor
+
+
+def test_sass_has_pair_cluster_and_bulk_copy_paths(built):
+    """cta_group::2 MMAs / TMA, cluster multicast and the bulk-copy BatchNorm kernels are really in the binary."""
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG.5D.2CTA", "UTMALDG.5D.MULTICAST", "UTCBAR.2CTA.MULTICAST", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_launch_plan_query_without_gpu(built):
+    """dg_conv_stats_rows is a pure host-side plan query (grid size = rows of the fused-statistics workspace): the
+    tile-selection rules can be checked here.  148 SMs are assumed when no device is present."""
+    rows = built.dg_conv_stats_rows
+    # deep 16->8 layer of the 512^2 step (B=32): 16 M tiles x 8 N tiles of 256 -> 128 CTAs (64 pairs), not 148 CTAs of
+    # 128-wide tiles
+    assert rows(0, 32, 8, 8, 2048, 1024) == 128
+    # wide layer with plenty of tiles: persistent grid on every SM, launched as 74 CTA pairs
+    assert rows(0, 32, 32, 32, 512, 256) == 148
+    # <= 128 output channels and many pixel tiles: role-swapped kernel, one CTA per SM
+    assert rows(0, 32, 128, 128, 128, 64) == 148
+    assert rows(1, 32, 128, 128, 128, 64) == 148
+    # tiny problem: one CTA per tile
+    assert 0 < rows(0, 2, 4, 4, 128, 64) <= 8
