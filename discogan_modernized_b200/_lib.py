@@ -5,6 +5,7 @@ source of truth for the C ABI.  There is no CPU fallback: if the library is miss
 first call raises.
 """
 import ctypes
+import hashlib
 import os
 import re
 import subprocess
@@ -49,21 +50,49 @@ def parse_header(text=None):
     return protos
 
 
+class ConvOpts(ctypes.Structure):
+    """``dg_conv_opts`` of the header: per-call options of the tensor-core convolutions."""
+    _fields_ = [("splitk_ws", ctypes.c_void_p), ("splitk_ws_bytes", ctypes.c_size_t), ("block_n", ctypes.c_int),
+                ("pair", ctypes.c_int), ("wgrad_pair", ctypes.c_int)]
+
+
+def source_hash():
+    """sha256 over the CUDA sources, their shared headers and the C-ABI header (what the library is compiled from)."""
+    h = hashlib.sha256()
+    for p in SOURCES + [PKG_DIR / "csrc" / "common.cuh", PKG_DIR / "csrc" / "tma_host.cuh", HEADER]:
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    return h.hexdigest()[:32]
+
+
+def built_hash():
+    """The source hash baked into the existing library (read from the file, without loading it), or None."""
+    if not LIB_PATH.exists():
+        return None
+    m = re.search(rb"dgsrc:([0-9a-f]{32})", LIB_PATH.read_bytes())
+    return m.group(1).decode() if m else None
+
+
 def build(force=False, verbose=False):
-    """Compile the CUDA sources for sm_100a into the in-tree shared library (nvcc cross-compiles
-    without a GPU)."""
-    if LIB_PATH.exists() and not force:
-        newest = max(p.stat().st_mtime for p in SOURCES + [PKG_DIR / "csrc" / "common.cuh", PKG_DIR / "csrc" / "tma_host.cuh"])
-        if LIB_PATH.stat().st_mtime >= newest:
-            return LIB_PATH
+    """Compile the CUDA sources for sm_100a into the in-tree shared library (nvcc cross-compiles without a GPU).
+    The library records the hash of the sources it was built from (``dg_source_hash()``); it is rebuilt whenever
+    that hash differs from the sources on disk, or when ``force`` / ``DG_FORCE_BUILD=1`` asks for it."""
+    want = source_hash()
+    force = force or os.environ.get("DG_FORCE_BUILD", "0") == "1"
+    if not force and built_hash() == want:
+        if verbose:
+            print(f"{LIB_PATH.name}: up to date (sources {want})")
+        return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
+    tmp = LIB_PATH.with_suffix(".so.tmp")
     cmd = [nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-O3", "-std=c++17", "-o", str(LIB_PATH)] + [str(s) for s in SOURCES]
+           "-O3", "-std=c++17", f"-I{HEADER.parent}", f'-DDG_SOURCE_HASH="dgsrc:{want}"', "-o", str(tmp)] + [str(s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd))
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise KernelError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 
@@ -83,6 +112,10 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the header declares something the .so lacks
             fn.restype = restype
             fn.argtypes = argtypes
+        got = L.dg_source_hash().decode()
+        if got != "dgsrc:" + source_hash() and os.environ.get("DG_ALLOW_STALE_LIB", "0") != "1":
+            raise KernelError(f"{LIB_PATH.name} was built from other sources ({got}) than the ones on disk "
+                              f"(dgsrc:{source_hash()}): rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")
         _lib = L
     return _lib
 

@@ -423,7 +423,8 @@ int dg_c3_down_tc(const void* xp, const void* wc, void* y, int B, int S, int act
   rc = make_map(&tmW, wc, 2, wd, wstr, wbox, 32);
   if (rc) return rc;
   const int smem_bytes = kDnWBytes + kDnStages * kDnStageBytes + 1024 + 256;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(c3_down_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
@@ -470,7 +471,8 @@ int dg_c3_wgrad_tc(const void* v64, const void* xp, float* dw, float beta, int B
   rc = make_patch_map(&tmP, xp, B, S, p.Wt, p.Ht, p.Bt);
   if (rc) return rc;
   const int smem_bytes = kWgStages * kWgStageBytes + 1024 + 256;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(c3_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {

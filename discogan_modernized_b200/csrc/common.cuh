@@ -5,7 +5,10 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <atomic>
 #include <utility>
+
+#include "discogan_b200.h"   // the C ABI: every extern "C" definition is checked against its declaration
 
 typedef __nv_bfloat16 bf16;
 
@@ -15,7 +18,16 @@ typedef __nv_bfloat16 bf16;
 #define DG_ERR_ARCH 3
 
 void dg_set_error(const char* fmt, ...);
-extern unsigned long long g_dg_launches;  // kernels launched through this library (bench.py's gpu_launches)
+extern std::atomic<unsigned long long> g_dg_launches;  // kernels launched through this library (bench.py's gpu_launches)
+
+// Per-device caches (kernel attributes, SM count) are indexed by the current device ordinal: one process may drive
+// several GPUs.
+constexpr int kMaxDevices = 64;
+static inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
 
 #define DG_CHECK_ARG(cond, ...)                 \
   do {                                          \
@@ -27,7 +39,7 @@ extern unsigned long long g_dg_launches;  // kernels launched through this libra
 
 #define DG_CHECK_LAUNCH(name)                                             \
   do {                                                                    \
-    ++g_dg_launches;                                                      \
+    g_dg_launches.fetch_add(1, std::memory_order_relaxed);                \
     cudaError_t e__ = cudaGetLastError();                                 \
     if (e__ != cudaSuccess) {                                             \
       dg_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
@@ -93,7 +105,7 @@ static inline void dg_launch(void (*kernel)(KArgs...), const DgCfg& c, Args&&...
   (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors surface in DG_CHECK_LAUNCH
 }
 
-enum { DG_ACT_NONE = 0, DG_ACT_LRELU = 1, DG_ACT_RELU = 2 };
+// DG_ACT_* activation codes come from discogan_b200.h
 
 // ---------------------------------------------------------------------------
 // small numeric helpers

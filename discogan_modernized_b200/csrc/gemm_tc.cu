@@ -938,8 +938,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmS, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
-// EXPERIMENTAL (DG_WGRAD_PAIR=1, off by default; written at the end of round 1, NOT yet run on hardware): the wgrad GEMM
-// as CTA pairs.  Two CTAs (m-tiles 2mp, 2mp+1 of one n-tile / tap half / split) issue M = 256 tcgen05.mma.cta_group::2:
+// wgrad GEMM as CTA pairs (default for layers with Cs % 256 == 0; DG_WGRAD_PAIR=0 falls back to the multicast cluster
+// kernel above).  Validated on B200 against tests/test_kernels_gpu.py -k wgrad; +35-45 % on the mid layers at 512x512.  Two CTAs (m-tiles 2mp, 2mp+1 of one n-tile / tap half / split) issue M = 256 tcgen05.mma.cta_group::2:
 // each CTA loads its own 128 cs rows of `small` and only FOUR of the eight tap boxes of `big` -- the N = 256 operand of
 // MMA group g (taps 4g..4g+3) is split across the pair, CTA r supplying taps 4g+2r, 4g+2r+1 -- so an SM ingests 24 KB
 // per 32-pixel chunk instead of 40 KB (the existing cluster mode multicasts the boxes: same L2 reads, but every SM still
@@ -1152,14 +1152,13 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
 // ------------------------------------------------------------------------------------------------
 // host side (tensor-map helpers live in tma_host.cuh)
 // ------------------------------------------------------------------------------------------------
-// split-K workspace registered by the host (dg_conv_set_splitk_workspace); split-K is off without it
-float* g_splitk_ws = nullptr;
-size_t g_splitk_ws_bytes = 0;
-// test hooks (dg_conv_set_tiling): force the N tile (0 = heuristic) and switch CTA pairs (-1 = default / DG_GEMM_PAIR)
-int g_force_bn = 0;      // 1 = force the role-swapped kernel wherever it is eligible
-int g_force_pair = -1;
-
+// Per-call options (dg_conv_opts in the header; NULL = defaults).  The library keeps no mutable launch state: the split-K
+// workspace and the tiling overrides travel with the call, kernel attributes and the SM count are cached per device.
 struct ConvGemmExtras {
+  float* splitk_ws = nullptr;  // fp32 workspace for split-K; split-K is off without it
+  size_t splitk_ws_bytes = 0;
+  int force_bn = 0;            // test hook: N tile (0 = heuristic; 1 = the role-swapped kernel wherever it is eligible)
+  int force_pair = -1;         // test hook: CTA pairs (-1 = default / DG_GEMM_PAIR)
   const void* mask = nullptr;
   float mask_slope = 0.f;
   float* img = nullptr;  // when set: Cb (mode 1 output channels) is the padded 16 and only 3 planes are written
@@ -1239,10 +1238,10 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   }
   const double gflop_all = 2.0 * B * Hs * Ws * (double)Cs * Cb * 16 * 1e-9;
   const int k_iters_all = (mode == 0 ? 16 : 4) * ((mode == 0 ? Cb : Cs) / 64);
-  if (!img_mode && !ex.mask && g_splitk_ws && gflop_all > sk_gflop && k_iters_all >= 2 * sk_mink && N % 256 == 0 &&
+  if (!img_mode && !ex.mask && ex.splitk_ws && gflop_all > sk_gflop && k_iters_all >= 2 * sk_mink && N % 256 == 0 &&
       (long long)m_tiles * (N / 256) * 2 <= num_sms())
     bn = 256;
-  if (g_force_bn > 1 && !img_mode && N % g_force_bn == 0) bn = g_force_bn;
+  if (ex.force_bn > 1 && !img_mode && N % ex.force_bn == 0) bn = ex.force_bn;
   // narrow layers (<= 128 output channels): role-swapped kernel, weights as M, 256 pixels as N
   static int swap_mode = -1;
   if (swap_mode < 0) {
@@ -1251,8 +1250,8 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   }
   const int tiles_plane = p.tiles_w * p.tiles_h * p.tiles_b;
   const bool swap_ok = !img_mode && (N == 64 || N == 128) && tiles_plane % 2 == 0;
-  const bool use_swap = swap_ok && g_force_bn != 64 && g_force_bn != 128 &&
-                        (g_force_bn == 1 || (swap_mode && m_tiles / 2 >= (num_sms() * 7) / 8));
+  const bool use_swap = swap_ok && ex.force_bn != 64 && ex.force_bn != 128 &&
+                        (ex.force_bn == 1 || (swap_mode && m_tiles / 2 >= (num_sms() * 7) / 8));
   if (use_swap) bn = N;
   p.block_n = bn;
   p.n_tiles = N / bn;
@@ -1286,14 +1285,14 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   while (!img_mode && p.nacc * 2 <= nacc_mode && p.nacc * 2 * bn <= kAccStride) p.nacc *= 2;
   const double gflop = 2.0 * B * Hs * Ws * (double)Cs * Cb * 16 * 1e-9;
   const size_t ws_need = (size_t)B * p.Ho * p.Wo * N * sizeof(float);
-  if (!use_swap && !img_mode && !ex.mask && g_splitk_ws && ws_need <= g_splitk_ws_bytes && gflop > sk_gflop &&
+  if (!use_swap && !img_mode && !ex.mask && ex.splitk_ws && ws_need <= ex.splitk_ws_bytes && gflop > sk_gflop &&
       p.num_tiles * 2 <= num_sms() && p.k_iters >= 2 * sk_mink) {
     int splits = num_sms() / p.num_tiles;
     if (splits > p.k_iters / sk_mink) splits = p.k_iters / sk_mink;
     if (splits > 1) {
       p.kps = dg_ceil_div(p.k_iters, splits);
       p.splits = dg_ceil_div(p.k_iters, p.kps);
-      p.ws = g_splitk_ws;
+      p.ws = ex.splitk_ws;
     }
   }
   // CTA pairs (cta_group::2) whenever two consecutive M tiles of one parity plane exist and half an N tile is still
@@ -1304,7 +1303,7 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     pair_mode = e ? atoi(e) : 1;
   }
   const int tiles_per_plane = p.tiles_w * p.tiles_h * p.tiles_b;
-  const int want_pair = g_force_pair >= 0 ? g_force_pair : pair_mode;
+  const int want_pair = ex.force_pair >= 0 ? ex.force_pair : pair_mode;
   const int ncta = (!use_swap && want_pair && !img_mode && bn >= 64 && tiles_per_plane % 2 == 0) ? 2 : 1;
   int work = (p.num_tiles / ncta) * p.splits;
   if (use_swap) work = p.num_tiles / 2;
@@ -1338,7 +1337,8 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     rc = make_weight_map(&tmB, wpacked, Cb, 16 * Cs, use_swap ? N : bn / ncta);
   }
   if (rc) return rc;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
@@ -1394,64 +1394,76 @@ void wgrad_plan(int B, int Hs, int Ws, int Cs, int Cb, WgradParams* p) {
 
 }  // namespace
 
+static ConvGemmExtras extras_from(const dg_conv_opts* o) {
+  ConvGemmExtras ex;
+  if (o) {
+    ex.splitk_ws = reinterpret_cast<float*>(o->splitk_ws);
+    ex.splitk_ws_bytes = o->splitk_ws_bytes;
+    ex.force_bn = o->block_n;
+    ex.force_pair = o->pair;
+  }
+  return ex;
+}
+
 extern "C" {
 
+int dg_conv_opts_check(const dg_conv_opts* o) {
+  if (!o) return DG_OK;
+  DG_CHECK_ARG(o->block_n == 0 || o->block_n == 1 || o->block_n == 64 || o->block_n == 128 || o->block_n == 256,
+               "conv opts: block_n=%d", o->block_n);
+  DG_CHECK_ARG(o->pair >= -1 && o->pair <= 1 && o->wgrad_pair >= -1 && o->wgrad_pair <= 1, "conv opts: pair=%d wgrad_pair=%d",
+               o->pair, o->wgrad_pair);
+  DG_CHECK_ARG(((uintptr_t)o->splitk_ws & 15) == 0, "conv opts: split-K workspace must be 16-byte aligned");
+  return DG_OK;
+}
+
 int dg_conv4x4s2_fprop(const void* x, const void* wd, void* z, int B, int H, int W, int Cb, int Cs,
-                       cudaStream_t stream) {
+                       const dg_conv_opts* opts, cudaStream_t stream) {
   DG_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "fprop: H=%d W=%d must be even", H, W);
-  return launch_conv_gemm(0, x, wd, z, B, H / 2, W / 2, Cs, Cb, stream);
+  if (int rc = dg_conv_opts_check(opts)) return rc;
+  return launch_conv_gemm(0, x, wd, z, B, H / 2, W / 2, Cs, Cb, stream, extras_from(opts));
 }
 
 int dg_conv4x4s2_dgrad(const void* dz, const void* wu, void* dx, int B, int Hs, int Ws, int Cs, int Cb,
-                       cudaStream_t stream) {
-  return launch_conv_gemm(1, dz, wu, dx, B, Hs, Ws, Cs, Cb, stream);
-}
-
-// Register a device workspace for split-K (fp32 [output pixels][N] of the largest split layer; 64 MB covers the
-// 512x512 family).  NULL/0 disables split-K.  The buffer is used by launches on any stream in program order.
-int dg_conv_set_tiling(int block_n, int pair) {
-  DG_CHECK_ARG(block_n == 0 || block_n == 1 || block_n == 64 || block_n == 128 || block_n == 256,
-               "conv tiling: block_n=%d", block_n);
-  g_force_bn = block_n;
-  g_force_pair = pair;
-  return DG_OK;
-}
-
-int dg_conv_set_splitk_workspace(void* ws, size_t bytes) {
-  g_splitk_ws = reinterpret_cast<float*>(ws);
-  g_splitk_ws_bytes = ws ? bytes : 0;
-  return DG_OK;
+                       const dg_conv_opts* opts, cudaStream_t stream) {
+  if (int rc = dg_conv_opts_check(opts)) return rc;
+  return launch_conv_gemm(1, dz, wu, dx, B, Hs, Ws, Cs, Cb, stream, extras_from(opts));
 }
 
 // Forward convolutions with the BatchNorm statistics of their output fused in the epilogue.
 // mode 0 = Conv2d fprop (x big -> z small), mode 1 = ConvTranspose2d fprop (x small -> z big).
 // stat_part: float[2 * rows * N] with rows = dg_conv_stats_rows(...), N = output channels; feed dg_bn_stats_finalize.
-int dg_conv_stats_rows(int mode, int B, int Hs, int Ws, int Cs, int Cb) {
+int dg_conv_stats_rows(int mode, int B, int Hs, int Ws, int Cs, int Cb, const dg_conv_opts* opts) {
   int grid = 0;
-  ConvGemmExtras ex;
+  if (dg_conv_opts_check(opts)) return 0;
+  ConvGemmExtras ex = extras_from(opts);
+  if (ex.splitk_ws_bytes && !ex.splitk_ws) ex.splitk_ws = reinterpret_cast<float*>(16);   // plan query without a buffer
   ex.grid_out = &grid;
   if (launch_conv_gemm(mode, (const void*)16, (const void*)16, (void*)16, B, Hs, Ws, Cs, Cb, 0, ex) != DG_OK) return 0;
   return grid;
 }
 int dg_conv4x4s2_fprop_stats(const void* x, const void* wd, void* z, float* stat_part, int B, int H, int W, int Cb,
-                             int Cs, cudaStream_t stream) {
+                             int Cs, const dg_conv_opts* opts, cudaStream_t stream) {
   DG_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && stat_part, "fprop_stats: bad args");
-  ConvGemmExtras ex;
+  if (int rc = dg_conv_opts_check(opts)) return rc;
+  ConvGemmExtras ex = extras_from(opts);
   ex.stat_part = stat_part;
   return launch_conv_gemm(0, x, wd, z, B, H / 2, W / 2, Cs, Cb, stream, ex);
 }
 int dg_convT4x4s2_fprop_stats(const void* x_small, const void* wu, void* y_big, float* stat_part, int B, int Hs, int Ws,
-                              int Cs, int Cb, cudaStream_t stream) {
+                              int Cs, int Cb, const dg_conv_opts* opts, cudaStream_t stream) {
   DG_CHECK_ARG(stat_part != nullptr, "convT_fprop_stats: bad args");
-  ConvGemmExtras ex;
+  if (int rc = dg_conv_opts_check(opts)) return rc;
+  ConvGemmExtras ex = extras_from(opts);
   ex.stat_part = stat_part;
   return launch_conv_gemm(1, x_small, wu, y_big, B, Hs, Ws, Cs, Cb, stream, ex);
 }
 
 // dgrad whose consumer is a BN-less LeakyReLU layer: dx = dgrad * (mask > 0 ? 1 : slope), mask = that layer's output
 int dg_conv4x4s2_dgrad_masked(const void* dz, const void* wu, void* dx, const void* mask, float slope, int B, int Hs,
-                              int Ws, int Cs, int Cb, cudaStream_t stream) {
-  ConvGemmExtras ex;
+                              int Ws, int Cs, int Cb, const dg_conv_opts* opts, cudaStream_t stream) {
+  if (int rc = dg_conv_opts_check(opts)) return rc;
+  ConvGemmExtras ex = extras_from(opts);
   ex.mask = mask;
   ex.mask_slope = slope;
   return launch_conv_gemm(1, dz, wu, dx, B, Hs, Ws, Cs, Cb, stream, ex);
@@ -1477,7 +1489,8 @@ size_t dg_conv4x4s2_wgrad_workspace(int B, int Hs, int Ws, int Cs, int Cb) {
 }
 
 int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
-                       int Cb, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                       int Cb, void* ws, size_t ws_bytes, const dg_conv_opts* opts, cudaStream_t stream) {
+  if (int rc = dg_conv_opts_check(opts)) return rc;
   DG_CHECK_ARG(B > 0 && is_pow2(Hs) && is_pow2(Ws), "wgrad: B=%d Hs=%d Ws=%d must be positive / powers of two", B, Hs,
                Ws);
   DG_CHECK_ARG(Cs % 128 == 0 && Cb % 64 == 0, "wgrad: Cs=%d must be a multiple of 128 and Cb=%d of 64", Cs, Cb);
@@ -1512,7 +1525,8 @@ int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta
   if (rc) return rc;
   rc = make_parity_map(&tmBig33, big, B, 2 * Hs, 2 * Ws, Cb, p.share ? 33 : p.Wt, p.Ht, p.Bt);
   if (rc) return rc;
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
@@ -1529,13 +1543,15 @@ int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta
     cluster_mode = e ? atoi(e) : 1;
   }
   p.cluster = (cluster_mode && !p.share && p.m_tiles % 2 == 0) ? 1 : 0;
-  static int pair_mode = -1;   // experimental cta_group::2 variant, see wgrad_gemm_pair_kernel
+  static int pair_mode = -1;   // cta_group::2 variant, see wgrad_gemm_pair_kernel
   if (pair_mode < 0) {
     const char* e = getenv("DG_WGRAD_PAIR");
-    pair_mode = e ? atoi(e) : 0;
+    pair_mode = e ? atoi(e) : 1;
   }
-  if (pair_mode && p.cluster && !p.debug) {
-    static bool pair_attr_set = false;
+  const int want_wpair = (opts && opts->wgrad_pair >= 0) ? opts->wgrad_pair : pair_mode;
+  if (want_wpair && p.cluster && !p.debug) {
+    static bool pair_attr_set_dev[kMaxDevices] = {};
+    bool& pair_attr_set = pair_attr_set_dev[current_device()];
     if (!pair_attr_set) {
       cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) {
@@ -1559,16 +1575,16 @@ int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta
 
 // ConvTranspose2d(ci,co,4,2,1) is the same three GEMMs with the roles swapped (model.py:118-138).
 int dg_convT4x4s2_fprop(const void* x_small, const void* wu, void* y_big, int B, int Hs, int Ws, int Cs, int Cb,
-                        cudaStream_t stream) {
-  return launch_conv_gemm(1, x_small, wu, y_big, B, Hs, Ws, Cs, Cb, stream);
+                        const dg_conv_opts* opts, cudaStream_t stream) {
+  return dg_conv4x4s2_dgrad(x_small, wu, y_big, B, Hs, Ws, Cs, Cb, opts, stream);
 }
 int dg_convT4x4s2_dgrad(const void* dy_big, const void* wd, void* dx_small, int B, int H, int W, int Cb, int Cs,
-                        cudaStream_t stream) {
-  return dg_conv4x4s2_fprop(dy_big, wd, dx_small, B, H, W, Cb, Cs, stream);
+                        const dg_conv_opts* opts, cudaStream_t stream) {
+  return dg_conv4x4s2_fprop(dy_big, wd, dx_small, B, H, W, Cb, Cs, opts, stream);
 }
 int dg_convT4x4s2_wgrad(const void* x_small, const void* dy_big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
-                        int Cb, void* ws, size_t ws_bytes, cudaStream_t stream) {
-  return dg_conv4x4s2_wgrad(x_small, dy_big, dw, beta, B, Hs, Ws, Cs, Cb, ws, ws_bytes, stream);
+                        int Cb, void* ws, size_t ws_bytes, const dg_conv_opts* opts, cudaStream_t stream) {
+  return dg_conv4x4s2_wgrad(x_small, dy_big, dw, beta, B, Hs, Ws, Cs, Cb, ws, ws_bytes, opts, stream);
 }
 
 }  // extern "C"

@@ -13,7 +13,7 @@
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-unsigned long long g_dg_launches = 0;
+std::atomic<unsigned long long> g_dg_launches{0};
 
 void dg_set_error(const char* fmt, ...) {
   va_list ap;
@@ -748,7 +748,8 @@ bool bn_stream_plan(long long P, int C, int nstreams, int sms, BnStreamPlan* pl)
 
 template <int MODE>
 int bn_stream_launch(const BnStreamParams& p, const BnStreamPlan& pl, cudaStream_t stream) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kMaxDevices] = {};
+  bool& attr_set = attr_set_dev[current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(bn_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) {
@@ -1007,15 +1008,15 @@ int ew_grid(long long work_items, int sms) {
   return (int)blocks;
 }
 
-int g_sms = 0;
 int sms() {
-  if (!g_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sms <= 0) g_sms = 148;
+  static int n_dev[kMaxDevices] = {};
+  const int dev = current_device();
+  int& n = n_dev[dev];
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
   }
-  return g_sms;
+  return n;
 }
 
 }  // namespace
@@ -1023,8 +1024,12 @@ int sms() {
 extern "C" {
 
 const char* dg_last_error(void) { return g_err; }
-int dg_version(void) { return 1; }
-long long dg_launch_count(void) { return (long long)g_dg_launches; }
+int dg_version(void) { return 2; }
+#ifndef DG_SOURCE_HASH
+#define DG_SOURCE_HASH "unknown"
+#endif
+const char* dg_source_hash(void) { return DG_SOURCE_HASH; }
+long long dg_launch_count(void) { return (long long)g_dg_launches.load(std::memory_order_relaxed); }
 
 // Fails loudly unless the current device is a Blackwell sm_100 part with a loadable kernel image.
 int dg_device_check(void) {

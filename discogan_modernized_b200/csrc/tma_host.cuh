@@ -73,10 +73,10 @@ static inline int make_weight_map(CUtensorMap* m, const void* base, int rows, in
 }
 
 static inline int num_sms() {
-  static int n = 0;
+  static int n_dev[kMaxDevices] = {};
+  const int dev = current_device();
+  int& n = n_dev[dev];
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }

@@ -167,8 +167,12 @@ class DiscoGANTrainer:
         if self.device.index is not None:
             torch.cuda.set_device(self.device)
         ops.device_check()
+        # launch context of this trainer: lanes, scratch buffers and split-K workspaces are its own, so several trainers
+        # (or host threads) in one process never share mutable state
+        self.ctx = ops.OpsContext()
         if os.environ.get("DISCOGAN_B200_SPLITK", "1") != "0":
-            ops.enable_splitk(self.device)
+            with ops.use_context(self.ctx):
+                ops.enable_splitk(self.device)
         self.image_size = image_size
         self.model_arch = model_arch
         loss_coefficients(model_arch, 0.5)  # validates
@@ -200,6 +204,7 @@ class DiscoGANTrainer:
         use_lanes = os.environ.get("DISCOGAN_B200_LANES", "1") != "0"
         self._side = torch.cuda.Stream(device=self.device) if use_lanes else None          # lane 1
         self._more = [torch.cuda.Stream(device=self.device) for _ in range(4)] if use_lanes else []   # lanes 2..5
+        self._deferred = None       # stepped networks of a step(..., defer_update=True) awaiting apply_update()
         self._graph_launches = {}   # kernels inside each captured graph
         self.kernel_launches = 0    # kernels of this library launched (eagerly or by graph replay) by step()
 
@@ -224,18 +229,32 @@ class DiscoGANTrainer:
             fm_out.zero_()
         return dict(ctx_r=ctx_r, ctx_f=ctx_f, p_real=p_real, p_fake=p_fake, diffs=diffs, feats_f=feats_f)
 
-    def step(self, A, B):
+    def step(self, A, B, defer_update=False):
         """One iteration on a batch pair (fp32 NCHW on the trainer's device).  Returns True if it was a
-        discriminator step.  Losses of the iteration are in ``self.loss_buf`` (see ``losses()``)."""
+        discriminator step.  Losses of the iteration are in ``self.loss_buf`` (see ``losses()``).
+
+        ``defer_update=True`` stops after the backward pass (eager launches, no gradient exchange, no Adam): the
+        stepped networks' gradients are in their flat buffers and ``apply_update()`` finishes the iteration.  This is
+        the seam an external reducer -- or a test emulating R data-parallel ranks in one process -- plugs into."""
+        with ops.use_context(self.ctx):
+            return self._step(A, B, defer_update)
+
+    def _step(self, A, B, defer_update):
         is_dis = self.iters % self.update_interval == 0
         rate = self.starting_rate if self.iters < self.gan_curriculum else self.default_rate
         from ._lib import lib
         count0 = lib().dg_launch_count()
+        if defer_update:
+            if self._deferred is not None:
+                raise RuntimeError("apply_update() has not been called for the previous deferred step")
+            self._deferred = self._forward_backward(A, B, is_dis, rate)
+            self.kernel_launches += lib().dg_launch_count() - count0
+            return is_dis
         if not self.use_graphs:
             self._step_impl(A, B, is_dis, rate)
             self.kernel_launches += lib().dg_launch_count() - count0
         else:
-            if self._scratch_gen != ops.scratch_generation and self._graphs:
+            if self._scratch_gen != self.ctx.generation and self._graphs:
                 self._graphs.clear()            # a scratch buffer moved: captured pointers are stale
                 self._eager_done.clear()
             key = (is_dis, rate, A.shape[0])
@@ -261,11 +280,27 @@ class DiscoGANTrainer:
                         self._step_impl(st[0], st[1], is_dis, rate)
                     self._graphs[key] = g
                     self._graph_launches[key] = lib().dg_launch_count() - count0
-                    self._scratch_gen = ops.scratch_generation
+                    self._scratch_gen = self.ctx.generation
                 g.replay()
                 self.kernel_launches += self._graph_launches[key]
         self.iters += 1
         return is_dis
+
+    def stepped_nets(self):
+        """Networks whose gradients the pending deferred step produced (in Adam order)."""
+        if self._deferred is None:
+            raise RuntimeError("no deferred step pending")
+        return list(self._deferred)
+
+    def apply_update(self, grad_scale=1.0):
+        """Finish a ``step(..., defer_update=True)``: Adam on the stepped networks with gradients scaled by
+        ``grad_scale`` (1/R when the flat gradient buffers hold a sum over R shards)."""
+        if self._deferred is None:
+            raise RuntimeError("no deferred step pending")
+        stepped, self._deferred = self._deferred, None
+        with ops.use_context(self.ctx):
+            self._update(stepped, grad_scale)
+        self.iters += 1
 
     # ------------------------------------------------------------------------------------------
     # two "lanes" (streams): the A->B->A and B->A->B halves of the step are independent between a few join points,
@@ -287,14 +322,28 @@ class DiscoGANTrainer:
         if i == 0 or self._side is None:
             yield
             return
-        ops.set_lane(i)
+        self.ctx.lane = i
         try:
             with torch.cuda.stream(self._streams()[i - 1]):
                 yield
         finally:
-            ops.set_lane(0)
+            self.ctx.lane = 0
 
     def _step_impl(self, A, B, is_dis, rate):
+        stepped = self._forward_backward(A, B, is_dis, rate, reduce=True)
+        self.reducer.join()
+        self._update(stepped, self.reducer.grad_scale)
+
+    def _update(self, stepped, grad_scale):
+        self._fork()
+        for i, n in enumerate(stepped):
+            with self._lane(i):
+                self.flat[n].adam(self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, grad_scale)
+        self._join()
+
+    def _forward_backward(self, A, B, is_dis, rate, reduce=False):
+        """All eight forwards, the losses and the backward passes that reach an optimiser step.  Returns the stepped
+        networks; with ``reduce`` their flat gradients are handed to the data-parallel reducer as they complete."""
         co = loss_coefficients(self.model_arch, rate)
         G_A, G_B, D_A, D_B = self.G_A, self.G_B, self.D_A, self.D_B
         save_g = not is_dis
@@ -305,7 +354,7 @@ class DiscoGANTrainer:
         l2, l3 = (2, 3) if small else (0, 1)
         nf = 4
         if small and is_dis:     # the discriminators' early backward: weight gradients on lanes 4/5
-            ops._wgrad_streams = {2: (self._more[2], 4), 3: (self._more[3], 5)}
+            self.ctx.wgrad_streams = {2: (self._more[2], 4), 3: (self._more[3], 5)}
             nf = 6
         fork(nf)
         with lane(0):
@@ -356,7 +405,7 @@ class DiscoGANTrainer:
         with lane(l3):
             db = fake_pass(D_B, real_b, AB, 1)
         join(nf)
-        ops._wgrad_streams = {}
+        self.ctx.wgrad_streams = {}
 
         red = self.reducer
         # backward: lanes 0/1 carry the two chains; for small images each chain's weight-gradient kernels go to its
@@ -365,11 +414,12 @@ class DiscoGANTrainer:
         wl = os.environ.get("DISCOGAN_B200_WGRAD_LANES", "auto")
         if self._side is not None and (wl == "1" or (wl == "auto" and self.image_size <= 128)):
             # (lanes 2/3 carry the discriminators' fake-pass backward at the same time, hence lanes 4/5 here)
-            ops._wgrad_streams = {0: (self._more[2], 4), 1: (self._more[3], 5)}
+            self.ctx.wgrad_streams = {0: (self._more[2], 4), 1: (self._more[3], 5)}
             nb = 6
         if is_dis:
-            for D in stepped:                                    # backward already done beside the forward passes
-                red.launch(self.flat[D].flat_g)
+            if reduce:
+                for D in stepped:                                # backward already done beside the forward passes
+                    red.launch(self.flat[D].flat_g)
         else:
             use_a = co["gen_A"] != 0.0 or co["fm_A"] != 0.0      # losses through D_A(BA): reach G_A pass 1
             use_b = co["gen_B"] != 0.0 or co["fm_B"] != 0.0      # losses through D_B(AB): reach G_B pass 1
@@ -410,15 +460,11 @@ class DiscoGANTrainer:
                 if g1 is not None:
                     generator_backward(G_A, c_ga1, g1, need_dx=False, need_wgrad=True, dout2=g2)
             join(nb)
-            for G in stepped:
-                red.launch(self.flat[G].flat_g)
-        ops._wgrad_streams = {}
-        red.join()
-        fork()
-        for i, n in enumerate(stepped):
-            with lane(i):
-                self.flat[n].adam(self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, red.grad_scale)
-        join()
+            if reduce:
+                for G in stepped:
+                    red.launch(self.flat[G].flat_g)
+        self.ctx.wgrad_streams = {}
+        return stepped
 
     def _disc_fake_backward(self, D, d, c_gen, c_fm, B):
         """Back-prop c_gen*gen_loss + c_fm*fm_loss through the fake pass of D down to its input image."""

@@ -26,9 +26,13 @@ typedef struct CUstream_st* dg_stream_t; /* == cudaStream_t */
 
 enum { DG_ACT_NONE = 0, DG_ACT_LRELU = 1, DG_ACT_RELU = 2 };
 
-/* ---- runtime ---- */
+/* ---- runtime ----
+ * The library keeps no mutable launch state: everything a launch depends on is an argument.  What is process-wide is
+ * the launch counter (atomic), dg_last_error (thread-local) and per-device caches of immutable facts (SM count,
+ * kernel attributes).  Any number of host threads / trainers / devices may call in concurrently. */
 const char* dg_last_error(void);
 int dg_version(void);
+const char* dg_source_hash(void); /* sha256 of the CUDA sources this library was compiled from (set by the build) */
 int dg_device_check(void); /* non-zero unless the current device is sm_100 */
 long long dg_launch_count(void); /* kernels launched through this library so far (process-wide) */
 
@@ -44,41 +48,51 @@ int dg_nhwc_bf16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, dg_s
 int dg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int HW, int C, dg_stream_t stream);
 
 /* ---- tensor-core implicit-GEMM convolutions (tcgen05 + TMEM + TMA) ----
- * nn.Conv2d(ci,co,4,2,1,bias=False) forward, model.py:11-31,84-103 (cuDNN fprop in the reference) */
+ * Per-call options, passed by pointer (NULL = all defaults):
+ *   splitk_ws / splitk_ws_bytes  device fp32 workspace [output pixels][N] for split-K of the small-M / large-K layers;
+ *                                NULL disables split-K.  Must not be shared by launches that can run concurrently.
+ *   block_n   test hook: force the GEMM N tile (64/128/256; 0 = heuristic; 1 = the role-swapped kernel for <= 128
+ *             output channels wherever it is eligible)
+ *   pair      test hook: CTA pairs (tcgen05 cta_group::2, two M tiles per MMA): 1/0, -1 = default (on)
+ *   wgrad_pair  same for the weight-gradient kernel (cta_group::2 pair kernel vs multicast cluster kernel)
+ * Results do not depend on block_n / pair / wgrad_pair (bit-identical except for split-K summation order). */
+typedef struct dg_conv_opts {
+  void* splitk_ws;
+  size_t splitk_ws_bytes;
+  int block_n;
+  int pair;
+  int wgrad_pair;
+} dg_conv_opts;
+int dg_conv_opts_check(const dg_conv_opts* opts); /* 0 if the options are well-formed */
+/* nn.Conv2d(ci,co,4,2,1,bias=False) forward, model.py:11-31,84-103 (cuDNN fprop in the reference) */
 int dg_conv4x4s2_fprop(const void* x_big, const void* wd, void* z_small, int B, int H, int W, int Cb, int Cs,
-                       dg_stream_t stream);
+                       const dg_conv_opts* opts, dg_stream_t stream);
 /* its data gradient (cuDNN bwd-data); also nn.ConvTranspose2d(ci,co,4,2,1) forward, model.py:118-138 */
 int dg_conv4x4s2_dgrad(const void* dz_small, const void* wu, void* dx_big, int B, int Hs, int Ws, int Cs, int Cb,
-                       dg_stream_t stream);
-/* device workspace for split-K of the small-M / large-K layers (fp32 [output pixels][N]); NULL disables split-K */
-int dg_conv_set_splitk_workspace(void* ws, size_t bytes);
-/* test hook: force the GEMM N tile (64/128/256, 0 = heuristic, 1 = the role-swapped kernel for <= 128 output
- * channels wherever it is eligible) and the use of CTA pairs -- tcgen05 cta_group::2, two
- * M tiles per MMA -- (1/0, -1 = default: on, env DG_GEMM_PAIR=0 turns it off).  Results do not depend on either. */
-int dg_conv_set_tiling(int block_n, int pair);
+                       const dg_conv_opts* opts, dg_stream_t stream);
 /* forward convolutions with the BatchNorm statistics of the output fused in the epilogue: stat_part = float[2*rows*N]
  * (rows = dg_conv_stats_rows, N = output channels) holds per-CTA partial sums / sums of squares of the fp32
  * accumulators; finish with dg_bn_stats_finalize.  mode 0 = Conv2d fprop, 1 = ConvTranspose2d fprop.
  * dg_conv_stats_rows returns 0 for shapes that run split-K (use dg_conv4x4s2_fprop + dg_bn_stats there). */
-int dg_conv_stats_rows(int mode, int B, int Hs, int Ws, int Cs, int Cb);
+int dg_conv_stats_rows(int mode, int B, int Hs, int Ws, int Cs, int Cb, const dg_conv_opts* opts);
 int dg_conv4x4s2_fprop_stats(const void* x_big, const void* wd, void* z_small, float* stat_part, int B, int H, int W,
-                             int Cb, int Cs, dg_stream_t stream);
+                             int Cb, int Cs, const dg_conv_opts* opts, dg_stream_t stream);
 int dg_convT4x4s2_fprop_stats(const void* x_small, const void* wu, void* y_big, float* stat_part, int B, int Hs, int Ws,
-                              int Cs, int Cb, dg_stream_t stream);
+                              int Cs, int Cb, const dg_conv_opts* opts, dg_stream_t stream);
 /* same, fused with the LeakyReLU derivative of the (BN-less) layer that produced x: dx *= (mask>0 ? 1 : slope) */
 int dg_conv4x4s2_dgrad_masked(const void* dz_small, const void* wu, void* dx_big, const void* mask, float slope, int B,
-                              int Hs, int Ws, int Cs, int Cb, dg_stream_t stream);
+                              int Hs, int Ws, int Cs, int Cb, const dg_conv_opts* opts, dg_stream_t stream);
 /* weight gradient (cuDNN bwd-filter): dw[Cs][Cb][4][4] = beta*dw + sum small (x) big; needs a workspace */
 size_t dg_conv4x4s2_wgrad_workspace(int B, int Hs, int Ws, int Cs, int Cb);
 int dg_conv4x4s2_wgrad(const void* small, const void* big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
-                       int Cb, void* ws, size_t ws_bytes, dg_stream_t stream);
+                       int Cb, void* ws, size_t ws_bytes, const dg_conv_opts* opts, dg_stream_t stream);
 /* ConvTranspose2d(4,2,1) aliases: forward == dgrad, dgrad == fprop, wgrad == wgrad(small = x, big = dy) */
 int dg_convT4x4s2_fprop(const void* x_small, const void* wu, void* y_big, int B, int Hs, int Ws, int Cs, int Cb,
-                        dg_stream_t stream);
+                        const dg_conv_opts* opts, dg_stream_t stream);
 int dg_convT4x4s2_dgrad(const void* dy_big, const void* wd, void* dx_small, int B, int H, int W, int Cb, int Cs,
-                        dg_stream_t stream);
+                        const dg_conv_opts* opts, dg_stream_t stream);
 int dg_convT4x4s2_wgrad(const void* x_small, const void* dy_big, float* dw, float beta, int B, int Hs, int Ws, int Cs,
-                        int Cb, void* ws, size_t ws_bytes, dg_stream_t stream);
+                        int Cb, void* ws, size_t ws_bytes, const dg_conv_opts* opts, dg_stream_t stream);
 
 /* ---- image-side 3-channel layers (direct kernels, fp32 NCHW image <-> bf16 NHWC 64 channels) ----
  * nn.Conv2d(3,64,4,2,1)+LeakyReLU(0.2), model.py:8-9,80-81 */

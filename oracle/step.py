@@ -62,6 +62,9 @@ class OracleStep:
                                     lr=lr, betas=(beta1, beta2), weight_decay=0.00001)   # :282-287
         self.iters = 0
 
+    def nets(self):
+        return self.G_A, self.G_B, self.D_A, self.D_B
+
     def losses(self, A, B):
         """Forward graph of image_translation.py:342-382; returns dict of tensors."""
         G_A, G_B, D_A, D_B, dev = self.G_A, self.G_B, self.D_A, self.D_B, self.device
@@ -97,18 +100,59 @@ class OracleStep:
                     fm_loss_A=fm_A, fm_loss_B=fm_B, recon_loss_A=recon_A, recon_loss_B=recon_B,
                     dis_loss_A=dis_A, dis_loss_B=dis_B, AB=AB, BA=BA, ABA=ABA, BAB=BAB)
 
-    def step(self, A, B, grad_hook=None):
-        """image_translation.py:336-390.  ``grad_hook(nets)`` runs between backward and
-        optimizer.step() (used to emulate the DDP gradient average)."""
+    def backward(self, A, B):
+        """zero_grad + forward + backward of the loss this iteration steps on (image_translation.py:336-364,385-390
+        without the optimiser call).  Returns the logged scalars."""
         for n in (self.G_A, self.G_B, self.D_A, self.D_B):
             n.zero_grad()
         out = self.losses(A, B)
         is_dis = self.iters % self.update_interval == 0
         (out["dis_loss"] if is_dis else out["gen_loss"]).backward()
-        if grad_hook is not None:
-            grad_hook((self.G_A, self.G_B, self.D_A, self.D_B))
-        (self.optim_dis if is_dis else self.optim_gen).step()
-        self.iters += 1
         logged = {k: float(v.detach()) for k, v in out.items() if k.endswith(("_A", "_B")) and v.dim() == 0}
         logged["is_dis_step"] = is_dis
         return logged
+
+    def apply(self):
+        """optimizer.step() of the stepped group (image_translation.py:385-390) and the iteration counter."""
+        is_dis = self.iters % self.update_interval == 0
+        (self.optim_dis if is_dis else self.optim_gen).step()
+        self.iters += 1
+
+    def step(self, A, B, grad_hook=None):
+        """image_translation.py:336-390.  ``grad_hook(nets)`` runs between backward and
+        optimizer.step() (used to emulate the DDP gradient average)."""
+        logged = self.backward(A, B)
+        if grad_hook is not None:
+            grad_hook((self.G_A, self.G_B, self.D_A, self.D_B))
+        self.apply()
+        return logged
+
+
+class OracleDataParallel:
+    """Single-process emulation of the reference's R-rank DDP step (distributed_image_translation.py:396-404,
+    465-518 with the broadcast_buffers crash of SURVEY.md F4 avoided): R replicas start from the same weights, each
+    runs forward/backward on its own shard with its own BatchNorm statistics and feature-matching means, parameter
+    gradients are averaged over replicas (DDP's all-reduce mean), every replica takes the same Adam step."""
+
+    def __init__(self, make_step, world):
+        self.replicas = [make_step(r) for r in range(world)]
+        ref = [list(n.parameters()) for n in self.replicas[0].nets()]
+        for st in self.replicas[1:]:                    # DDP constructor: rank 0's weights everywhere
+            for net, ps in zip(st.nets(), ref):
+                for p, q in zip(net.parameters(), ps):
+                    p.data.copy_(q.data)
+
+    def step(self, shards):
+        """shards[r] = (A_r, B_r).  Returns the per-replica logged scalars."""
+        logs = [st.backward(A, B) for st, (A, B) in zip(self.replicas, shards)]
+        R = len(self.replicas)
+        plists = [[p for n in st.nets() for p in n.parameters()] for st in self.replicas]
+        for ps in zip(*plists):
+            if ps[0].grad is None:
+                continue
+            mean = sum(p.grad for p in ps) / R
+            for p in ps:
+                p.grad = mean.clone()
+        for st in self.replicas:
+            st.apply()
+        return logs

@@ -21,14 +21,31 @@ def test_header_parses_every_declaration():
     assert declared == set(protos), declared ^ set(protos)
     assert len(protos) >= 38
     assert protos["dg_last_error"][0].__name__ == "c_char_p"
-    assert len(protos["dg_conv4x4s2_wgrad"][1]) == 12
+    assert len(protos["dg_conv4x4s2_wgrad"][1]) == 13      # ..., ws, ws_bytes, opts, stream
 
 
 def test_library_exports_all_symbols(built):
     for name in _lib.parse_header():
         assert hasattr(built, name), name
-    assert built.dg_version() >= 1
+    assert built.dg_version() >= 2
     assert built.dg_launch_count() == 0
+    # the library records the sources it was compiled from; _lib.lib() refuses a stale one
+    assert built.dg_source_hash().decode() == "dgsrc:" + _lib.source_hash() == "dgsrc:" + _lib.built_hash()
+
+
+def test_no_global_setters_in_the_abi():
+    """Round-1's process-global setters are gone: launch options travel with each call (dg_conv_opts)."""
+    import ctypes
+    protos = _lib.parse_header()
+    assert "dg_conv_set_splitk_workspace" not in protos and "dg_conv_set_tiling" not in protos
+    text = _lib.HEADER.read_text()
+    m = re.search(r"typedef struct dg_conv_opts \{(.*?)\} dg_conv_opts;", text, flags=re.S)
+    fields = [f.strip().split()[-1] for f in m.group(1).split(";") if f.strip()]
+    assert fields == [n for n, _ in _lib.ConvOpts._fields_]
+    assert ctypes.sizeof(_lib.ConvOpts) == 32
+    bad = _lib.ConvOpts(None, 0, 77, -1, -1)
+    assert _lib.lib().dg_conv_opts_check(ctypes.byref(bad)) != 0
+    assert _lib.lib().dg_conv_opts_check(None) == 0
 
 
 def test_no_torch_or_cudnn_in_the_abi(built):
@@ -66,7 +83,8 @@ def test_sass_has_pair_cluster_and_bulk_copy_paths(built):
 def test_launch_plan_query_without_gpu(built):
     """dg_conv_stats_rows is a pure host-side plan query (grid size = rows of the fused-statistics workspace): the
     tile-selection rules can be checked here.  148 SMs are assumed when no device is present."""
-    rows = built.dg_conv_stats_rows
+    import ctypes
+    rows = lambda *a: built.dg_conv_stats_rows(*a, None)
     # deep 16->8 layer of the 512^2 step (B=32): 16 M tiles x 8 N tiles of 256 -> 128 CTAs (64 pairs), not 148 CTAs of
     # 128-wide tiles
     assert rows(0, 32, 8, 8, 2048, 1024) == 128
@@ -77,3 +95,8 @@ def test_launch_plan_query_without_gpu(built):
     assert rows(1, 32, 128, 128, 128, 64) == 148
     # tiny problem: one CTA per tile
     assert 0 < rows(0, 2, 4, 4, 128, 64) <= 8
+    # the deepest 512^2 layer at B=32 is SM-starved (4 M tiles x 8 N tiles): with a split-K workspace on offer the plan
+    # splits (no fused statistics: 0 rows); without one it does not
+    sk = _lib.ConvOpts(None, 64 << 20, 0, -1, -1)
+    assert built.dg_conv_stats_rows(0, 32, 4, 4, 2048, 2048, ctypes.byref(sk)) == 0
+    assert rows(0, 32, 4, 4, 2048, 2048) > 0

@@ -112,11 +112,19 @@ def test_conv_up(impl, B, H, Cb, Cs):
     assert rel_l2(to_nchw_f32(out), ref) < 4e-3
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("impl", ["simt", "tc", "tc_cluster"])
 @pytest.mark.parametrize("B,H,Cb,Cs", CONV_SHAPES)
 def test_conv_wgrad(impl, B, H, Cb, Cs):
+    """tc = the default plan (cta_group::2 pair kernel where Cs % 256 == 0), tc_cluster = the multicast-cluster kernel
+    (dg_conv_opts.wgrad_pair = 0)."""
     ops = ops_mod()
     Hs = H // 2
+    if impl == "tc_cluster":
+        ops.set_conv_tiling(0, -1, wgrad_pair=0)
+        try:
+            return test_conv_wgrad("tc", B, H, Cb, Cs)
+        finally:
+            ops.set_conv_tiling(0, -1, -1)
     if impl == "simt" and B * H * H * Cs * Cb > 2e10 / 16:
         pytest.skip("simt reference kernel too slow for this shape")
     big = rnd(B, Cb, H, H, seed=5).to(BF16)
@@ -429,8 +437,7 @@ def test_conv_splitk_deep_layer():
         up = ops.conv_up(to_nhwc_bf16(s.float()), wu)
         assert rel_l2(to_nchw_f32(up), refu) < 4e-3
     finally:
-        ops._splitk_enabled.clear()
-        ops._splitk_select(xn.device)
+        ops.current().splitk_bytes.clear()
 
 
 @pytest.mark.parametrize("bn", [128, 256])
