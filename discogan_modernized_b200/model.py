@@ -182,12 +182,19 @@ def _bn_act_bwd(dy, sv, bn, act, need_wgrad, dy2=None, bcast=None, bcast_coef=0.
     return dz.view(sv.z.shape)
 
 
-def _conv1_backward(pk, weight, ctx, dz1, need_dx, need_wgrad, dx_out, dx_accumulate):
+def _ready(grad_ready, *params):
+    """Tell the data-parallel reducer that the kernels producing these parameters' gradients (this pass) are enqueued."""
+    if grad_ready is not None:
+        grad_ready(params)
+
+
+def _conv1_backward(pk, weight, ctx, dz1, need_dx, need_wgrad, dx_out, dx_accumulate, grad_ready=None):
     """Backward of the image-side Conv2d(3,64,4,2,1)+LeakyReLU given dz1 = d(loss)/d(pre-activation)."""
     if need_wgrad:
         ctx.keep.append(dz1)
         with ops.wgrad_side():
             ops.c3_wgrad_tc(dz1, ctx.xp, *_grad_buf(weight))
+        _ready(grad_ready, weight)
     if not need_dx:
         return None
     _, wu3 = pk.get_c3(weight)
@@ -229,9 +236,10 @@ def discriminator_forward(mod, x, save=True):
 
 
 def discriminator_backward(mod, ctx, dlogit, dfeats=None, fm_bcast=None, need_dx=True, need_wgrad=True,
-                           dx_out=None, dx_accumulate=False):
+                           dx_out=None, dx_accumulate=False, grad_ready=None):
     """dlogit fp32 [B]; dfeats[i] optional bf16 NHWC grads on feats; fm_bcast[i] optional (diff, coef).
-    Returns d(loss)/d(input image) (fp32 NCHW) or None."""
+    Returns d(loss)/d(input image) (fp32 NCHW) or None.  ``grad_ready(params)`` is called, deepest layer first, as soon
+    as the kernels writing those parameters' gradients are enqueued (the bucketed gradient exchange hangs off it)."""
     pk = mod._packed
     B = ctx.B
     head = getattr(mod, f"conv{mod.n_down + 1}")
@@ -242,6 +250,7 @@ def discriminator_backward(mod, ctx, dlogit, dfeats=None, fm_bcast=None, need_dx
         ctx.keep.append(dl)
         with ops.wgrad_side():
             ops.fc_wgrad(dl, y_last.view(B, -1), *_grad_buf(head.weight))
+        _ready(grad_ready, head.weight)
     dy = ops.fc_up(dl, wd.view(1, -1)).view(y_last.shape)
     for k in range(mod.n_down, 1, -1):
         i = k - 2
@@ -255,10 +264,11 @@ def discriminator_backward(mod, ctx, dlogit, dfeats=None, fm_bcast=None, need_dx
             ctx.keep.append(dz)
             with ops.wgrad_side():
                 ops.conv_wgrad(dz, y_prev, *_grad_buf(conv.weight))
+            _ready(grad_ready, conv.weight, bn.weight, bn.bias)
         _, wu = pk.get(conv.weight, True, True)
         # the gradient reaching conv1's output also takes conv1's LeakyReLU derivative (fused in the epilogue)
         dy = ops.conv_up(dz, wu, mask=ctx.y1 if i == 0 else None, slope=LRELU_SLOPE)
-    return _conv1_backward(pk, mod.conv1.weight, ctx, dy, need_dx, need_wgrad, dx_out, dx_accumulate)
+    return _conv1_backward(pk, mod.conv1.weight, ctx, dy, need_dx, need_wgrad, dx_out, dx_accumulate, grad_ready)
 
 
 class _DiscFn(torch.autograd.Function):
@@ -391,8 +401,10 @@ def generator_forward(mod, x, save=True):
     return out, ctx
 
 
-def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=None, dx_accumulate=False, dout2=None):
-    """dout (+ dout2): d(loss)/d(output image), fp32 NCHW.  Returns d(loss)/d(input image) or None."""
+def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=None, dx_accumulate=False, dout2=None,
+                       grad_ready=None):
+    """dout (+ dout2): d(loss)/d(output image), fp32 NCHW.  Returns d(loss)/d(input image) or None.
+    ``grad_ready(params)``: see discriminator_backward."""
     pk = mod._packed
     B = ctx.B
     enc_convs, enc_bns, head_conv, head_bn, dec_convs, dec_bns = _gen_layers(mod)
@@ -403,6 +415,7 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
         ctx.keep.append(dpre)
         with ops.wgrad_side():
             ops.c3_wgrad_tc(dec_in[-1].y, dpre, *_grad_buf(last.weight))
+        _ready(grad_ready, last.weight)
     wc_last, _ = pk.get_c3(last.weight)
     dy = ops.c3_down_tc(dpre, wc_last, ops.ACT_NONE)
     for j in range(len(ctx.dec), 0, -1):
@@ -414,6 +427,7 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
             ctx.keep.append(dz)
             with ops.wgrad_side():
                 ops.conv_wgrad(x_in, dz, *_grad_buf(conv.weight))      # convT wgrad: small = input, big = dz
+            _ready(grad_ready, conv.weight, bn.weight, bn.bias)
         wd, _ = pk.get(conv.weight, True, True)
         dy = ops.conv_down(dz, wd)                                      # convT dgrad
     # decoder.0: ConvTranspose2d(100, C, 4, 1, 0)
@@ -423,6 +437,7 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
         ctx.keep.append(dz)
         with ops.wgrad_side():
             ops.fc_wgrad(ctx.head.y, dz.view(B, -1), *_grad_buf(dec_convs[0].weight))
+        _ready(grad_ready, dec_convs[0].weight, dec_bns[0].weight, dec_bns[0].bias)
     dy = ops.fc_down(dz.view(B, -1), wd0.view(wd0.shape[0], -1))
     # encoder head: Conv2d(C, 100, 4, 1, 0)
     dz = _bn_act_bwd(dy, ctx.head, head_bn, ACT_LRELU, need_wgrad)
@@ -431,6 +446,7 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
         ctx.keep.append(dz)
         with ops.wgrad_side():
             ops.fc_wgrad(dz, y_last.view(B, -1), *_grad_buf(head_conv.weight))
+        _ready(grad_ready, head_conv.weight, head_bn.weight, head_bn.bias)
     wdh, _ = pk.get(head_conv.weight, True, False)
     dy = ops.fc_up(dz, wdh.view(wdh.shape[0], -1)).view(y_last.shape)
     for i in range(len(ctx.enc), 0, -1):
@@ -442,9 +458,10 @@ def generator_backward(mod, ctx, dout, need_dx=True, need_wgrad=True, dx_out=Non
             ctx.keep.append(dz)
             with ops.wgrad_side():
                 ops.conv_wgrad(dz, y_prev, *_grad_buf(conv.weight))
+            _ready(grad_ready, conv.weight, bn.weight, bn.bias)
         _, wu = pk.get(conv.weight, True, True)
         dy = ops.conv_up(dz, wu, mask=ctx.y1 if i == 1 else None, slope=LRELU_SLOPE)
-    return _conv1_backward(pk, enc_convs[0].weight, ctx, dy, need_dx, need_wgrad, dx_out, dx_accumulate)
+    return _conv1_backward(pk, enc_convs[0].weight, ctx, dy, need_dx, need_wgrad, dx_out, dx_accumulate, grad_ready)
 
 
 class _GenFn(torch.autograd.Function):

@@ -11,11 +11,13 @@ as one hand-scheduled forward/backward over the kernel engines in ``model.py``:
 * GAN-BCE, reconstruction-MSE and feature-matching losses are fused kernels; loss weights are host
   constants so no autograd graph is built;
 * parameters, gradients and Adam moments of each network live in flat fp32 buffers: Adam is one
-  kernel per network and the data-parallel exchange is one NCCL all-reduce per network, issued on a
-  side stream as soon as that network's last backward pass has been enqueued (overlapping the
-  remaining backward work); gradients are averaged over ranks, BatchNorm statistics stay per rank,
-  the learning rate is not scaled (``distributed_image_translation.py:396-427`` semantics with the
-  ``broadcast_buffers`` crash of SURVEY.md F4 avoided);
+  kernel per network; the data-parallel exchange is bucketed like the reference's DDP reducer
+  (``distributed_image_translation.py:401-404,513-518``): the flat gradient of a stepped network is cut
+  into contiguous buckets in backward-completion order and each bucket's NCCL all-reduce is launched on
+  a side stream the moment the kernels writing its last gradient are enqueued, overlapping the rest of
+  the backward pass (``GradReducer``); gradients are averaged over ranks, BatchNorm statistics stay per
+  rank, the learning rate is not scaled (``distributed_image_translation.py:396-427`` semantics with
+  the ``broadcast_buffers`` crash of SURVEY.md F4 avoided);
 * the whole iteration (several hundred kernel launches, micro-seconds each at 64x64) is captured once
   per (step kind, loss weights) into a CUDA graph and replayed: inputs are copied into static
   buffers, the Adam step counter lives on the device.
@@ -88,34 +90,152 @@ class FlatNet:
         return int(self.adam_state[0].item())
 
 
-class GradReducer:
-    """Average flat gradient buffers over the data-parallel group.  CUDA: NCCL all-reduce on a side
-    stream ordered after the producing kernels, joined before Adam.  CPU tensors (gloo, tests): blocking."""
+def plan_buckets(sizes, cap_elems):
+    """Partition parameters (given by their padded element counts in registration order) into contiguous buckets in
+    BACKWARD-completion order, i.e. walking the registration order from the end (the last-registered layers finish
+    their backward first).  A bucket closes once it holds >= cap_elems.  Returns [(first_param, last_param)] index
+    pairs (inclusive), first-finishing bucket first."""
+    buckets, hi, acc = [], len(sizes) - 1, 0
+    for i in range(len(sizes) - 1, -1, -1):
+        acc += sizes[i]
+        if acc >= cap_elems or i == 0:
+            buckets.append((i, hi))
+            hi, acc = i - 1, 0
+    return buckets
 
-    def __init__(self, group=None, enabled=True):
+
+class GradReducer:
+    """Data-parallel gradient exchange (reference: the DDP reducer, distributed_image_translation.py:396-404,513-518).
+
+    Each stepped network's flat fp32 gradient is cut into contiguous buckets in backward-completion order
+    (``plan_buckets``; cap = min(25 MiB -- DDP's default --, a third of the network)).  The backward pass reports every
+    layer's parameters as soon as the kernels writing their final gradients are enqueued (``hook``); when a bucket is
+    complete its NCCL all-reduce (sum; the 1/world factor is folded into Adam) is launched on a side stream ordered
+    after exactly those kernels, so the exchange of the deep layers overlaps the backward of the shallow ones -- inside
+    the captured CUDA graph as well.  ``join`` makes the optimiser wait for all buckets.  The two lanes of the step use
+    two communicators, so one network's last bucket never queues behind the other's first.
+    CPU tensors (gloo, tests): blocking all-reduce per bucket."""
+
+    DDP_BUCKET_BYTES = 25 << 20
+
+    def __init__(self, group=None, enabled=True, bucket_bytes=None):
         self.enabled = enabled and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.group = group
         self.world = dist.get_world_size(group) if self.enabled else 1
-        self._stream = None
+        env = os.environ.get("DISCOGAN_B200_BUCKET_MB")
+        self.bucket_bytes = bucket_bytes if bucket_bytes is not None else (int(float(env) * (1 << 20)) if env else None)
+        self._streams = {}       # comm slot -> side stream
+        self._groups = {0: group}
         self._pending = []
+        self._state = {}         # FlatNet -> dict(buckets, left, passes, slot)
+        self.launched = []       # (net numel, lo, hi) of every all-reduce issued (tests / accounting)
 
-    def launch(self, flat_g):
-        """Start summing flat_g over ranks (the 1/world factor is folded into Adam's grad_scale)."""
+    # -- planning -------------------------------------------------------------------------------------
+    def _plan(self, flat):
+        plan = getattr(flat, "_buckets", None)
+        if plan is None:
+            sizes = [(p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN for p in flat.params]
+            cap = self.bucket_bytes if self.bucket_bytes else min(self.DDP_BUCKET_BYTES, -(-flat.numel * 4 // 3))
+            plan = []
+            for lo, hi in plan_buckets(sizes, max(1, cap // 4)):
+                plan.append((flat.offsets[lo], flat.offsets[hi] + sizes[hi], [id(p) for p in flat.params[lo:hi + 1]]))
+            flat._buckets = plan
+        return plan
+
+    def _group_for(self, slot, device_is_cuda):
+        """Communicator of a lane slot: slot 0 = the trainer's group, slot 1 = a second communicator over the same ranks
+        (created collectively on first use; every rank reaches this point in the same order)."""
+        if slot not in self._groups:
+            if not device_is_cuda or os.environ.get("DISCOGAN_B200_DP_COMMS", "2") == "1":
+                self._groups[slot] = self.group
+            else:
+                ranks = dist.get_process_group_ranks(self.group) if self.group is not None else None
+                self._groups[slot] = dist.new_group(ranks=ranks)
+        return self._groups[slot]
+
+    def prepare(self, flat_nets):
+        """Create the communicators and bucket plans outside the step (never during CUDA-graph capture)."""
         if not self.enabled:
             return
-        if flat_g.is_cuda:
-            if self._stream is None:
-                self._stream = torch.cuda.Stream()
-            ready = torch.cuda.Event()
-            ready.record(torch.cuda.current_stream())
-            with torch.cuda.stream(self._stream):
-                self._stream.wait_event(ready)
-                dist.all_reduce(flat_g, op=dist.ReduceOp.SUM, group=self.group)
-                done = torch.cuda.Event()
-                done.record(self._stream)
-            self._pending.append(done)
-        else:
-            dist.all_reduce(flat_g, op=dist.ReduceOp.SUM, group=self.group)
+        for i, fn in enumerate(flat_nets):
+            self._plan(fn)
+        if any(fn.flat_g.is_cuda for fn in flat_nets):
+            for slot in (0, 1):
+                self._group_for(slot, True)
+
+    # -- per-step protocol ----------------------------------------------------------------------------
+    def begin(self, flat, passes, slot=0):
+        """Start tracking one stepped network: every parameter will be reported ``passes`` times (once per backward
+        pass of this iteration); its buckets go to communicator ``slot``."""
+        if not self.enabled:
+            return
+        plan = self._plan(flat)
+        self._state[flat] = dict(left=[len(ids) * passes for _, _, ids in plan],
+                                 where={pid: b for b, (_, _, ids) in enumerate(plan) for pid in ids}, slot=slot)
+
+    def hook(self, flat):
+        """The ``grad_ready`` callback for the backward passes of this network (None when not reducing)."""
+        if not self.enabled or flat not in self._state:
+            return None
+        st = self._state[flat]
+        plan = flat._buckets
+
+        def grad_ready(params):
+            for p in params:
+                b = st["where"][id(p)]
+                st["left"][b] -= 1
+                if st["left"][b] == 0:
+                    lo, hi, _ = plan[b]
+                    self._launch(flat, lo, hi, st["slot"])
+        return grad_ready
+
+    def finish(self, flat):
+        """Launch whatever has not been reported complete (a safety net: every bucket is normally launched by the
+        hook) and stop tracking."""
+        st = self._state.pop(flat, None)
+        if st is None:
+            return
+        for b, left in enumerate(st["left"]):
+            if left > 0:
+                lo, hi, _ = flat._buckets[b]
+                self._launch(flat, lo, hi, st["slot"])
+
+    def _launch(self, flat, lo, hi, slot):
+        buf = flat.flat_g[lo:hi]
+        self.launched.append((flat.numel, lo, hi))
+        if not buf.is_cuda:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self._group_for(slot, False))
+            return
+        from . import ops
+        stream = self._streams.get(slot)
+        if stream is None:
+            stream = self._streams[slot] = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        ready = [torch.cuda.Event()]
+        ready[0].record(cur)                                   # dgamma / dbeta (and inline weight gradients)
+        ctx = ops.current()
+        side = ctx.wgrad_streams.get(ctx.lane)
+        if side is not None:                                   # weight-gradient kernels of this lane run on a side stream
+            ev = torch.cuda.Event()
+            ev.record(side[0])
+            ready.append(ev)
+        with torch.cuda.stream(stream):
+            for ev in ready:
+                stream.wait_event(ev)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self._group_for(slot, True))
+            done = torch.cuda.Event()
+            done.record(stream)
+        self._pending.append(done)
+
+    def launch(self, flat_g):
+        """Whole-buffer all-reduce (kept for callers that exchange a buffer in one piece)."""
+        if not self.enabled:
+            return
+        class _Whole:  # noqa: N801 -- minimal FlatNet stand-in
+            pass
+        w = _Whole()
+        w.flat_g, w.numel = flat_g, flat_g.numel()
+        self._launch(w, 0, flat_g.numel(), 0)
 
     def join(self):
         for ev in self._pending:
@@ -191,6 +311,7 @@ class DiscoGANTrainer:
         self.flat = {n: FlatNet(n) for n in (self.G_A, self.G_B, self.D_A, self.D_B)}
         self.reducer = GradReducer(process_group, enabled=data_parallel)
         self.reducer.broadcast_params(self.flat.values())
+        self.reducer.prepare(list(self.flat.values()))
         self.loss_buf = torch.zeros(len(LOSS_NAMES), dtype=torch.float32, device=self.device)
         self.iters = 0
         if use_graphs is None:
@@ -366,25 +487,30 @@ class DiscoGANTrainer:
         # after its forward, in the reference's accumulation order (real, then fake), beside the generator forwards.
         d_coef = {0: co["dis_A"], 1: co["dis_B"]}
         stepped = []
+        red = self.reducer
         if is_dis:
-            for D, c in ((D_A, co["dis_A"]), (D_B, co["dis_B"])):
+            for slot, (D, c) in enumerate(((D_A, co["dis_A"]), (D_B, co["dis_B"]))):
                 if c != 0.0:
                     self.flat[D].zero_grad()
                     stepped.append(D)
+                    if reduce:                   # two backward passes (real, fake) write every parameter
+                        red.begin(self.flat[D], passes=2, slot=slot)
 
         def real_pass(D, img, slot):
             real = discriminator_forward(D, img, save=is_dis)
             if is_dis and d_coef[slot] != 0.0:
                 p_real = ops.sigmoid_fwd(real[0])
                 dlr, _ = ops.gan_bce_bwd(p_real, p_real, d_coef[slot], 0.0, want_fake=False)
-                discriminator_backward(D, real[2], dlr, need_dx=False, need_wgrad=True)
+                discriminator_backward(D, real[2], dlr, need_dx=False, need_wgrad=True,
+                                       grad_ready=red.hook(self.flat[D]) if reduce else None)
             return real
 
         def fake_pass(D, real, img, slot):
             d = self._disc_fake_and_losses(D, real, img, slot)
             if is_dis and d_coef[slot] != 0.0:
                 _, dlf = ops.gan_bce_bwd(d["p_real"], d["p_fake"], d_coef[slot], 0.0, want_real=False)
-                discriminator_backward(D, d["ctx_f"], dlf, need_dx=False, need_wgrad=True)
+                discriminator_backward(D, d["ctx_f"], dlf, need_dx=False, need_wgrad=True,
+                                       grad_ready=red.hook(self.flat[D]) if reduce else None)
             return d
 
         with lane(l2):
@@ -407,7 +533,6 @@ class DiscoGANTrainer:
         join(nf)
         self.ctx.wgrad_streams = {}
 
-        red = self.reducer
         # backward: lanes 0/1 carry the two chains; for small images each chain's weight-gradient kernels go to its
         # own side stream (lanes 2/3) and overlap the dgrad chain
         nb = 2
@@ -417,9 +542,9 @@ class DiscoGANTrainer:
             self.ctx.wgrad_streams = {0: (self._more[2], 4), 1: (self._more[3], 5)}
             nb = 6
         if is_dis:
-            if reduce:
-                for D in stepped:                                # backward already done beside the forward passes
-                    red.launch(self.flat[D].flat_g)
+            if reduce:                          # backward already done beside the forward passes; buckets went out as each
+                for D in stepped:               # layer's fake-pass gradients were enqueued
+                    red.finish(self.flat[D])
         else:
             use_a = co["gen_A"] != 0.0 or co["fm_A"] != 0.0      # losses through D_A(BA): reach G_A pass 1
             use_b = co["gen_B"] != 0.0 or co["fm_B"] != 0.0      # losses through D_B(AB): reach G_B pass 1
@@ -429,6 +554,14 @@ class DiscoGANTrainer:
                 stepped.append(G_A)
             for G in stepped:
                 self.flat[G].zero_grad()
+            if reduce:                          # G_B's last pass runs on lane 0, G_A's on lane 1: one communicator each
+                n_b = int(co["recon_B"] != 0.0) + int(co["recon_A"] != 0.0 or use_b)
+                n_a = int(co["recon_A"] != 0.0) + int(co["recon_B"] != 0.0 or use_a)
+                if G_B in stepped:
+                    red.begin(self.flat[G_B], passes=n_b, slot=0)
+                if G_A in stepped:
+                    red.begin(self.flat[G_A], passes=n_a, slot=1)
+            hook = (lambda G: red.hook(self.flat[G])) if reduce else (lambda G: None)
             dAB = dBA = dAB_d = dBA_d = None
             fork(6 if small else nb)
             # phase A (lanes 2/3 for small images): the discriminators' fake passes, data gradients only -- independent of
@@ -444,25 +577,25 @@ class DiscoGANTrainer:
             with lane(0):
                 if co["recon_A"] != 0.0:
                     dABA = ops.mse_bwd(ABA, A, co["recon_A"])
-                    dAB = generator_backward(G_A, c_ga2, dABA, need_dx=True, need_wgrad=True)
+                    dAB = generator_backward(G_A, c_ga2, dABA, need_dx=True, need_wgrad=True, grad_ready=hook(G_A))
             with lane(1):
                 if co["recon_B"] != 0.0:
                     dBAB = ops.mse_bwd(BAB, B, co["recon_B"])
-                    dBA = generator_backward(G_B, c_gb2, dBAB, need_dx=True, need_wgrad=True)
+                    dBA = generator_backward(G_B, c_gb2, dBAB, need_dx=True, need_wgrad=True, grad_ready=hook(G_B))
             join(6 if small else nb); fork(nb)
             # phase C: the generators' first passes (each accumulates into the gradients its second pass just wrote)
             with lane(0):
                 g1, g2 = (dAB, dAB_d) if dAB is not None else (dAB_d, None)
                 if g1 is not None:
-                    generator_backward(G_B, c_gb1, g1, need_dx=False, need_wgrad=True, dout2=g2)
+                    generator_backward(G_B, c_gb1, g1, need_dx=False, need_wgrad=True, dout2=g2, grad_ready=hook(G_B))
             with lane(1):
                 g1, g2 = (dBA, dBA_d) if dBA is not None else (dBA_d, None)
                 if g1 is not None:
-                    generator_backward(G_A, c_ga1, g1, need_dx=False, need_wgrad=True, dout2=g2)
+                    generator_backward(G_A, c_ga1, g1, need_dx=False, need_wgrad=True, dout2=g2, grad_ready=hook(G_A))
             join(nb)
             if reduce:
                 for G in stepped:
-                    red.launch(self.flat[G].flat_g)
+                    red.finish(self.flat[G])
         self.ctx.wgrad_streams = {}
         return stepped
 

