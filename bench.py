@@ -6,9 +6,13 @@
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
 
 A step is one iteration of the reference loop (image_translation.py:335-390) on one synthetic A/B batch pair:
-D step when iter % 3 == 0, else G step; K is rounded to whole D,G,G cycles.  `value` is whole-job image-pairs/s
-with the batches already resident in HBM; `e2e` is the same loop fed from pinned host buffers with the H2D copy of
-both batches and a D2H read of the eight losses inside the timed region every step.
+D step when iter % 3 == 0, else G step; exactly K steps are timed (the D:G:G schedule simply continues across them)
+after exactly W warm-up steps.  Before the warm-up the trainer is primed for two D:G:G cycles (`config.prime_steps`):
+the first cycle runs eagerly and sizes the scratch buffers, the second captures the step graphs -- set-up, like building
+the model, not warm-up.  `value` is whole-job image-pairs/s with the batches already resident in HBM; `e2e` is the same
+loop fed from pinned host buffers with the H2D copy of both batches and a D2H read of the eight losses inside the timed
+region every step.  `also` repeats the measurement at 512x512, B=32 per GPU (BASELINE config 4) at every N;
+`inference` is the eval-mode AtoB generator sweep over batch sizes (config 5, N=1).
 """
 import argparse
 import json
@@ -34,8 +38,16 @@ def parse_args():
     ap.add_argument("--model-arch", default="discogan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--also-512", type=int, default=1, help="also report a short 512^2 B=32 measurement at N=1")
+    ap.add_argument("--also-512", type=int, default=1, help="also report a 512^2 B=32-per-GPU measurement (every N)")
+    ap.add_argument("--also-steps", type=int, default=12)
+    ap.add_argument("--no-inference", action="store_true", help="skip the eval-mode AtoB batch sweep")
     return ap.parse_args()
+
+
+def run_config(S, B, world, arch):
+    """The `config` object -- identical keys for the B200 arm and the reference arm."""
+    return {"workload": workload_name(S, B), "image_size": S, "batch_per_gpu": B, "global_batch": B * world,
+            "model_arch": arch, "parallelism": f"dp{world}"}
 
 
 def workload_name(S, B):
@@ -155,8 +167,8 @@ def run_reference(args, S, B):
         "impl": "reference", "metric": "train image-pairs/sec", "value": v, "unit": "image-pairs/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": max(1, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(S, B), "image_size": S, "batch_per_gpu": B, "sample_batch": Bs,
-                   "model_arch": args.model_arch},
+        "config": run_config(S, B, max(1, args.gpus), args.model_arch),
+        "details": {"sample_batch": Bs, "note": "CPU arm: rank 0 only, one process on all host cores"},
         "cpu_baseline": {"value": v, "unit": "image-pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "image-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -320,7 +332,7 @@ def measure_roofline(tr, batches, torch, pk):
         try:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(g):
+            with ops.use_context(tr.ctx), torch.cuda.graph(g):      # the trainer's launch plan (split-K workspaces, lanes)
                 keep = [fn(*a, **k) for _, _, fn, a, k in mine]
             g.replay()
             torch.cuda.synchronize()
@@ -408,78 +420,122 @@ def run_b200(args, S, B):
         Bt = torch.rand(batch, 3, image_size, image_size, generator=g)
         return A.to(device), Bt.to(device)
 
-    steps = max(1, args.steps)                 # exactly K timed steps; the D:G:G schedule simply continues across them
-    warmup = max(6, args.warmup)               # at least two D:G:G cycles: the first captures the step graphs, the second
-                                               # replays each of them once (first-replay upload) outside the timed region
-    tr = DiscoGANTrainer(image_size=S, device=f"cuda:{local}", model_arch=args.model_arch, seed=1234)
-    host = [tuple(t.pin_memory() for t in synthetic_batch(B, S, step=i, rank=rank)) for i in range(3)]
-    batches = [(a.cuda(non_blocking=True), b.cuda(non_blocking=True)) for a, b in host]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()                         # nvidia-smi needs ~0.1 s to deliver its first sample: start it early
-    for i in range(warmup):
-        tr.step(*batches[i % 3])
-    torch.cuda.synchronize()
-
-    L0 = tr.kernel_launches
-    sampler.mark_begin()
-    ms = timed_steps(tr, batches, steps, torch, dist, world)
-    launches = tr.kernel_launches - L0          # kernels of libdiscogan_b200.so (eager launches + graph-replayed nodes)
-    ms_e2e, h2d, d2h = timed_steps_e2e(tr, host, steps, torch, dist, world)
-    sampler.mark_end()
-    clocks = sampler.stop() if rank == 0 else None
-    pairs = B * world * steps
-    value = pairs / (ms * 1e-3)
+    PRIME = 6      # two D:G:G cycles of set-up: eager (buffer sizing, kernel attributes), then graph capture + first replay
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     pk = peaks()
+
+    def measure(size, bsz, n_steps, n_warmup, with_clocks):
+        """prime -> W warm-up steps -> K timed steps (device-resident batches) -> K timed steps fed from the host."""
+        tr = DiscoGANTrainer(image_size=size, device=f"cuda:{local}", model_arch=args.model_arch, seed=1234)
+        host = [tuple(t.pin_memory() for t in synthetic_batch(bsz, size, step=i, rank=rank)) for i in range(3)]
+        batches = [(a.cuda(non_blocking=True), b.cuda(non_blocking=True)) for a, b in host]
+        sampler = ClockSampler(local) if (with_clocks and rank == 0) else None
+        if sampler:
+            sampler.start()                     # nvidia-smi needs ~0.1 s to deliver its first sample: start it early
+        for i in range(PRIME + n_warmup):
+            tr.step(*batches[i % 3])
+        torch.cuda.synchronize()
+        L0 = tr.kernel_launches
+        if sampler:
+            sampler.mark_begin()
+        ms = timed_steps(tr, batches, n_steps, torch, dist, world)
+        launches = tr.kernel_launches - L0      # kernels of libdiscogan_b200.so (eager launches + graph-replayed nodes)
+        ms_e2e, h2d, d2h = timed_steps_e2e(tr, host, n_steps, torch, dist, world)
+        clocks = None
+        if sampler:
+            sampler.mark_end()
+            clocks = sampler.stop()
+        pairs = bsz * world * n_steps
+        res = {"value": pairs / (ms * 1e-3), "unit": "image-pairs/s", "ms_per_step": ms / n_steps, "steps": n_steps,
+               "warmup": n_warmup,
+               "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "image-pairs/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / n_steps},
+               "gpu_launches": int(launches)}
+        lanes = 1 + (1 + len(tr._more) if tr._side is not None else 0)
+        return tr, batches, res, clocks, lanes
+
+    tr, batches, res, clocks, lanes = measure(S, B, steps, warmup, True)
     line = {
-        "metric": "train image-pairs/sec", "value": value, "unit": "image-pairs/s", "n_gpus": world, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": workload_name(S, B), "image_size": S, "batch_per_gpu": B, "global_batch": B * world,
-                   "model_arch": args.model_arch, "parallelism": f"dp{world}", "cuda_graphs": bool(tr.use_graphs), "lanes": 1 + (1 + len(tr._more) if tr._side is not None else 0),
-                   "l2": "per-step working set (weights+grads+Adam moments+activations) exceeds the 126 MB L2; no explicit flush"},
-        "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "image-pairs/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / steps},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "metric": "train image-pairs/sec", "value": res["value"], "unit": "image-pairs/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": run_config(S, B, world, args.model_arch),
+        "details": {"prime_steps": PRIME, "cuda_graphs": bool(tr.use_graphs), "lanes": lanes,
+                    "grad_buckets": {n: len(getattr(tr.flat[net], "_buckets", []) or []) for n, net in
+                                     zip(("G_A", "G_B", "D_A", "D_B"), tr.nets())} if world > 1 else None,
+                    "l2": "per-step working set (weights+grads+Adam moments+activations) exceeds the 126 MB L2; no explicit flush",
+                    "library": {"version": _lib.lib().dg_version(), "sources": _lib.lib().dg_source_hash().decode()}},
+        "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clocks,
     }
+    if rank == 0 and world == 1 and not args.no_roofline:
+        roof, per_kernel = measure_roofline(tr, batches, torch, pk)
+        line["roofline"] = roof
+        line["kernels"] = per_kernel
+    tr.close()
+    del tr, batches
+    torch.cuda.empty_cache()
+    if args.also_512 and S != 512:
+        # BASELINE config 4 (512x512, B=32 per GPU) at the same N: every rank takes part (the gradient exchange is
+        # 1.8 GB per G step there), rank 0 reports
+        try:
+            tr5, b5, res5, _, _ = measure(512, 32, max(1, args.also_steps), 6, False)
+            also = {"workload": workload_name(512, 32), **res5}
+            if rank == 0 and world == 1 and not args.no_roofline:
+                also["roofline"], also["kernels"] = measure_roofline(tr5, b5, torch, pk)
+            tr5.close()
+            del tr5, b5
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            also = {"workload": workload_name(512, 32), "error": str(e)[:300]}
+        line["also"] = also
     if rank == 0 and world == 1:
-        if not args.no_roofline:
-            roof, per_kernel = measure_roofline(tr, batches, torch, pk)
-            line["roofline"] = roof
-            line["kernels"] = per_kernel
-        if args.also_512 and S != 512:
+        if not args.no_inference:
             try:
-                del tr, batches
-                torch.cuda.empty_cache()
-                tr5 = DiscoGANTrainer(image_size=512, device=f"cuda:{local}", model_arch=args.model_arch, seed=1234)
-                b5 = [synthetic_batch(32, 512, step=i, device="cuda") for i in range(3)]
-                for i in range(3):
-                    tr5.step(*b5[i])
-                ms5 = timed_steps(tr5, b5, 6, torch, dist, 1)
-                roof5, per5 = (measure_roofline(tr5, b5, torch, pk) if not args.no_roofline else (None, None))
-                line["also"] = {"workload": workload_name(512, 32), "value": 32 * 6 / (ms5 * 1e-3), "unit": "image-pairs/s",
-                                "ms_per_step": ms5 / 6, "steps": 6, "roofline": roof5, "kernels": per5}
-                del tr5, b5
-                torch.cuda.empty_cache()
+                line["inference"] = inference_sweep(torch, local)
             except Exception as e:  # noqa: BLE001
-                line["also"] = {"workload": workload_name(512, 32), "error": str(e)[:300]}
+                line["inference"] = {"error": str(e)[:300]}
         if not args.no_cpu_baseline:
             v, msc, cores, sample, _ = cpu_reference_pairs_per_s(S, B, 3, 1, args.model_arch, budget_s=60.0)
             line["cpu_baseline"] = {"value": v, "unit": "image-pairs/s", "cores": cores, "kind": "port", "sample": sample}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        # release the captured graphs before leaving; skip destroy_process_group (an NCCL communicator that was
-        # captured into CUDA graphs can block in teardown) -- exiting the process is the documented alternative
-        try:
-            tr.close()
-        except NameError:
-            pass
+        # skip destroy_process_group (an NCCL communicator that was captured into CUDA graphs can block in teardown) --
+        # exiting the process is the documented alternative
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()
         os._exit(0)
+
+
+def inference_sweep(torch, local):
+    """BASELINE config 5: eval-mode AtoB generator forward (inference.py:149,168-172 batched) over batch sizes, images
+    already on the device; CUDA events around `reps` back-to-back forwards after 3 warm-up calls."""
+    from discogan_modernized_b200.model import Generator
+    out = {"unit": "images/s", "direction": "AtoB", "mode": "eval (BatchNorm running statistics)", "sizes": {}}
+    for size, batches in ((64, (1, 2, 4, 8, 16, 32, 64, 128, 256)), (512, (1, 2, 4, 8, 16, 32, 64, 128, 256))):
+        torch.manual_seed(1234)
+        g = Generator(extra_layers=True, image_size=size).to(f"cuda:{local}").eval()
+        rows = {}
+        with torch.no_grad():
+            for bsz in batches:
+                x = torch.rand(bsz, 3, size, size, device=f"cuda:{local}")
+                for _ in range(3):
+                    g(x)
+                reps = max(3, min(50, int(2e4 / (bsz * (size / 64) ** 2))))
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                s.record()
+                for _ in range(reps):
+                    g(x)
+                e.record()
+                torch.cuda.synchronize()
+                ms = s.elapsed_time(e) / reps
+                rows[str(bsz)] = {"images_per_s": round(bsz / (ms * 1e-3), 1), "ms_per_batch": round(ms, 4)}
+        out["sizes"][str(size)] = rows
+        del g
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():

@@ -7,12 +7,13 @@ folders are absent; precedent batch_size_optimization.py:62-63) or read from two
 (``--data_A DIR --data_B DIR``, resized to --image_size, scaled to [0,1], CHW).
 """
 import argparse
+import sys
 from datetime import datetime
 from pathlib import Path
 
 import torch
 
-from .train_step import DiscoGANTrainer
+from .train_step import DiscoGANTrainer, LossReadback, format_log_line
 
 
 def build_parser(kind):
@@ -49,6 +50,14 @@ def build_parser(kind):
         for n in ("gen_A", "gen_B", "dis_A", "dis_B"):
             p.add_argument(f"--load_{n}", default=None)
     # additions (not in the reference)
+    p.add_argument("--resume", default=None, metavar="DIR[:TAG]",
+                   help="continue a run: loads gen_A/gen_B/dis_A/dis_B_{TAG}.pth and train_state_{TAG}.pth (Adam moments, "
+                        "iteration counter) from DIR; TAG defaults to 'final'")
+    p.add_argument("--sample_mode", default="reference", choices=["reference", "eval"],
+                   help="sample dumps: 'reference' keeps the generators in train mode under no_grad like the reference's "
+                        "save_sample_images (advances BatchNorm running statistics); 'eval' leaves training untouched")
+    p.add_argument("--n_samples", type=int, default=5, help="rows of the sample grid (reference: 5)")
+    p.add_argument("--deterministic", action="store_true", help="bit-reproducible iterations (slightly slower)")
     p.add_argument("--synthetic", action="store_true", help="uniform-random A/B batches")
     p.add_argument("--data_A", default=None)
     p.add_argument("--data_B", default=None)
@@ -98,10 +107,70 @@ class Batches:
 
 
 def save_models(tr, model_path, tag):
-    """gen_A_{tag}.pth ... -- the reference's checkpoint names and state-dict layout (image_translation.py:420-432)."""
+    """gen_A_{tag}.pth ... -- the reference's checkpoint names and state-dict layout (image_translation.py:420-432) --
+    plus train_state_{tag}.pth: Adam moments / step state and the iteration counter, so that --resume continues the run
+    (the reference restarts the optimiser and the GAN curriculum)."""
+    model_path = Path(model_path)
     model_path.mkdir(parents=True, exist_ok=True)
     for name, net in (("gen_A", tr.G_A), ("gen_B", tr.G_B), ("dis_A", tr.D_A), ("dis_B", tr.D_B)):
         torch.save({k: v.detach().cpu().clone() for k, v in net.state_dict().items()}, model_path / f"{name}_{tag}.pth")
+    torch.save(tr.training_state(), model_path / f"train_state_{tag}.pth")
+
+
+def load_models(tr, model_path, tag="final", with_state=True):
+    """Inverse of save_models.  Weights-only checkpoints written by the reference load too (with_state is then skipped
+    with a note, and Adam / the curriculum start over exactly as in the reference)."""
+    model_path = Path(model_path)
+    dev = tr.device
+    tr.load_weights({n: torch.load(model_path / f"{n}_{tag}.pth", map_location=dev)
+                     for n in ("gen_A", "gen_B", "dis_A", "dis_B")})
+    state = model_path / f"train_state_{tag}.pth"
+    if with_state and state.exists():
+        tr.load_training_state(torch.load(state, map_location="cpu"))
+        return True
+    if with_state:
+        print(f"note: {state} not found -- weights restored, optimiser state and iteration counter start over",
+              file=sys.stderr)
+    return False
+
+
+def warn_ignored(args):
+    """Flags of the reference parsers that select dataset subsets this re-host has no use for."""
+    for flag in ("style_B", "constraint", "constraint_type"):
+        if getattr(args, flag, None):
+            print(f"warning: --{flag} selects a CelebA attribute subset in the reference's dataset.py; this entry point reads "
+                  "--data_A/--data_B folders (or --synthetic) and ignores it", file=sys.stderr)
+    if getattr(args, "style_A", None):
+        print("note: --style_A only names the results/models sub-directory here (reference: also a CelebA attribute)",
+              file=sys.stderr)
+
+
+def test_batches(args, data, device):
+    """The fixed test tensors of the sample dumps (image_translation.py:236-252: n_test held-out images per domain;
+    distributed: 10, :369)."""
+    n = max(args.n_samples, 2)                           # train-mode BatchNorm over a 1x1 map needs >= 2 images
+    if data.A is not None:
+        A, B = data.A[-n:], data.B[-n:]
+    else:
+        g = torch.Generator().manual_seed(4321)
+        A = torch.rand(n, 3, args.image_size, args.image_size, generator=g)
+        B = torch.rand(n, 3, args.image_size, args.image_size, generator=g)
+    return A.to(device), B.to(device)
+
+
+def save_sample_grid(tr, test_A, test_B, save_dir, iteration, n_samples=5, mode="reference"):
+    """``save_sample_images`` (image_translation.py:170-208): rows of A, B, A->B, B->A, A->B->A, B->A->B written to
+    samples_iter_{iteration}.png (a plain image grid; the reference renders the same six columns with matplotlib)."""
+    from PIL import Image
+    AB, BA, ABA, BAB = tr.sample_images(test_A, test_B, mode)
+    n = min(n_samples, test_A.shape[0])
+    rows = [torch.cat([t[i].float().clamp(0, 1) for t in (test_A, test_B, AB, BA, ABA, BAB)], dim=2) for i in range(n)]
+    grid = torch.cat(rows, dim=1).mul(255).round().byte().permute(1, 2, 0).cpu().numpy()
+    save_dir = Path(save_dir)
+    save_dir.mkdir(parents=True, exist_ok=True)
+    out = save_dir / f"samples_iter_{iteration}.png"
+    Image.fromarray(grid).save(out)
+    return out
 
 
 def run_training(args, kind, rank=0, world=1, process_group=None):
@@ -110,44 +179,63 @@ def run_training(args, kind, rank=0, world=1, process_group=None):
     ts = datetime.now().strftime("%Y%m%d_%H%M%S") + (f"_rank{rank}" if kind == "distributed" else "")
     sub = Path(args.task_name) / (getattr(args, "style_A", None) or "") / args.model_arch / ts
     result_path, model_path = Path(args.results_dir) / sub, Path(args.models_dir) / sub
+    if rank == 0:
+        warn_ignored(args)
     if kind == "distributed":
         torch.manual_seed(1234)                       # distributed_image_translation.py:372
     tr = DiscoGANTrainer(image_size=args.image_size, device=device, model_arch=args.model_arch,
                          learning_rate=args.learning_rate, beta1=args.beta1, beta2=args.beta2,
                          update_interval=args.update_interval, gan_curriculum=args.gan_curriculum,
                          starting_rate=args.starting_rate, default_rate=args.default_rate, variant=variant,
-                         process_group=process_group)
-    if kind == "distributed":
-        for flag, net in (("load_gen_A", tr.G_A), ("load_gen_B", tr.G_B), ("load_dis_A", tr.D_A), ("load_dis_B", tr.D_B)):
-            path = getattr(args, flag)
-            if path:
-                net.load_state_dict(torch.load(path, map_location=device))
-                net._packed.invalidate()
+                         process_group=process_group, deterministic=args.deterministic)
+    if kind == "distributed":                          # reference :379-393: weights only
+        tr.load_weights({n: torch.load(getattr(args, f"load_{n}"), map_location=device) if getattr(args, f"load_{n}") else None
+                         for n in ("gen_A", "gen_B", "dis_A", "dis_B")})
+    if args.resume:
+        path, _, tag = args.resume.partition(":")
+        load_models(tr, path, tag or "final")
     data = Batches(args, rank, world)
     total = args.epochs * data.n_batches
     log = None
+    test_A = test_B = None
     if rank == 0:
         result_path.mkdir(parents=True, exist_ok=True)
-        log = open(result_path / "training_log.txt", "w")
+        log = open(result_path / "training_log.txt", "a" if args.resume else "w")
         log.write(f"Training started at {ts}\nTask: {args.task_name}, Model: {args.model_arch}\n"
                   f"Batch size: {args.batch_size}, Learning rate: {args.learning_rate}\n\n")
-    done = False
+        if args.image_save_interval > 0:
+            test_A, test_B = test_batches(args, data, device)
+    readback = LossReadback(tr.loss_buf)
+
+    def emit(done):
+        for it, losses in done:
+            line = format_log_line(it, total, losses)
+            print(line, flush=True)
+            log.write(line + "\n")
+
+    start_iter, done = tr.iters, False
     for epoch in range(args.epochs):
         for A, B in data.epoch(epoch):
             it = tr.iters
             tr.step(A.to(device, non_blocking=True), B.to(device, non_blocking=True))
-            if rank == 0 and it % args.log_interval == 0:
-                line = tr.log_line(total)
-                print(line, flush=True)
-                log.write(line + "\n")
-            if rank == 0 and it % args.model_save_interval == 0 and it > 0:
-                save_models(tr, model_path, it)
-            if args.max_iters is not None and tr.iters >= args.max_iters:
+            if rank == 0:
+                if it % args.log_interval == 0:            # image_translation.py:393-398, without stalling the GPU
+                    emit(readback.request(it))
+                emit(readback.poll())
+                if args.image_save_interval > 0 and it % args.image_save_interval == 0:     # :411-417 (incl. iteration 0)
+                    save_sample_grid(tr, test_A, test_B, result_path / "samples", it, args.n_samples, args.sample_mode)
+                if it % args.model_save_interval == 0 and (it > start_iter or it == 0):     # :420-424 (incl. iteration 0)
+                    save_models(tr, model_path, it)
+            if args.max_iters is not None and tr.iters - start_iter >= args.max_iters:
                 done = True
                 break
         if done:
             break
     if rank == 0:
+        emit(readback.drain())
         save_models(tr, model_path, "final")
         log.close()
+        print(f"Training completed. Final models saved to {model_path}")
+        print(f"Results and logs saved to {result_path}")
+    tr.result_path, tr.model_path = result_path, model_path
     return tr

@@ -23,7 +23,6 @@ from . import ops
 from .ops import ACT_LRELU, ACT_RELU
 
 LRELU_SLOPE = 0.2
-_FUSE_BN_STATS = os.environ.get("DISCOGAN_B200_FUSE_STATS", "1") != "0"   # debugging switch
 
 
 def family_channels(image_size: int):
@@ -145,7 +144,7 @@ def _bump_counters(mod, training):
 
 def _conv_bn(conv_fn, conv_stats_fn, x, w, training):
     """Run a GEMM convolution; in training mode its epilogue also produces the partial BatchNorm sums."""
-    if training and ops._conv_impl == "tc" and _FUSE_BN_STATS:
+    if training and ops._conv_impl == "tc" and ops.current().fuse_stats:
         return conv_stats_fn(x, w)
     return conv_fn(x, w), None
 

@@ -6,6 +6,7 @@ synchronously -- there is no CPU fallback.
 """
 import contextlib
 import ctypes
+import os
 import threading
 
 import torch
@@ -48,6 +49,9 @@ class OpsContext:
         self.splitk_bytes = {}       # device -> workspace size (split-K enabled on that device)
         self.splitk_ws = {}          # (device, lane) -> uint8 buffer
         self.block_n, self.pair, self.wgrad_pair = 0, -1, -1    # test hooks (dg_conv_opts)
+        # BatchNorm statistics from the conv epilogue's fp32 accumulators (shared-memory float atomics: the summation
+        # order, hence the last bit, varies from run to run); off = a separate deterministic statistics pass
+        self.fuse_stats = os.environ.get("DISCOGAN_B200_FUSE_STATS", "1") != "0"
         self._opts = {}
 
     def conv_opts(self, device, splitk=True):

@@ -255,6 +255,66 @@ class GradReducer:
             fn.net._packed.invalidate()
 
 
+def format_log_line(iteration, total_iterations, l):
+    """The reference's log line (image_translation.py:394-398), parsed by hyperparameter_search.py:269-271 with
+    ``GEN: (\\d+\\.\\d+)/(\\d+\\.\\d+)`` etc."""
+    return (f"Iter [{iteration}/{total_iterations}] "
+            f"GEN: {l['gen_loss_A']:.4f}/{l['gen_loss_B']:.4f}, "
+            f"FM: {l['fm_loss_A']:.4f}/{l['fm_loss_B']:.4f}, "
+            f"RECON: {l['recon_loss_A']:.4f}/{l['recon_loss_B']:.4f}, "
+            f"DIS: {l['dis_loss_A']:.4f}/{l['dis_loss_B']:.4f}")
+
+
+class LossReadback:
+    """Non-blocking readback of the eight logged losses: ``request(tag)`` enqueues a device->pinned-host copy behind the
+    step that produced them and returns immediately; ``poll()`` yields (tag, losses) for every copy that has landed
+    (``drain()`` waits for the rest).  The training loop never stalls the GPU to print a log line (the reference calls
+    ``.item()`` eight times per logged iteration, image_translation.py:394-398)."""
+
+    def __init__(self, loss_buf, slots=4):
+        self.buf = loss_buf
+        self.host = [torch.empty(len(LOSS_NAMES), dtype=torch.float32).pin_memory() for _ in range(slots)]
+        self.events = [torch.cuda.Event() for _ in range(slots)]
+        self.pending = []          # (slot, tag), oldest first
+        self.free = list(range(slots))
+
+    def request(self, tag):
+        out = []
+        if not self.free:          # ring full: wait for the oldest (never happens with log intervals >> ring size)
+            out = [self._take(wait=True)]
+        slot = self.free.pop()
+        self.host[slot].copy_(self.buf, non_blocking=True)
+        self.events[slot].record(torch.cuda.current_stream())
+        self.pending.append((slot, tag))
+        return out
+
+    def _take(self, wait):
+        slot, tag = self.pending[0]
+        if wait:
+            self.events[slot].synchronize()
+        elif not self.events[slot].query():
+            return None
+        self.pending.pop(0)
+        vals = dict(zip(LOSS_NAMES, self.host[slot].tolist()))
+        self.free.append(slot)
+        return tag, vals
+
+    def poll(self):
+        out = []
+        while self.pending:
+            r = self._take(wait=False)
+            if r is None:
+                break
+            out.append(r)
+        return out
+
+    def drain(self):
+        out = []
+        while self.pending:
+            out.append(self._take(wait=True))
+        return out
+
+
 def loss_coefficients(model_arch, rate):
     """d(gen_loss)/d(component) for image_translation.py:370-382.  Returns dict with keys
     gen_A/fm_A (through D_A's fake pass), gen_B/fm_B (through D_B's fake pass), recon_A, recon_B,
@@ -275,12 +335,12 @@ class DiscoGANTrainer:
 
     variant='angle_pairing' skips the first feature map in the FM loss and defaults both rates to 0.9
     (``angle_pairing.py:55-57,115``).  ``use_graphs``: replay captured CUDA graphs (default on; set
-    DISCOGAN_B200_GRAPHS=0 or pass False to launch every kernel eagerly)."""
+    DISCOGAN_B200_GRAPHS=0 or pass False to launch every kernel eagerly).  ``deterministic``: see below."""
 
     def __init__(self, image_size=512, device="cuda", model_arch="discogan", learning_rate=2e-4, beta1=0.5,
                  beta2=0.999, weight_decay=1e-5, update_interval=3, gan_curriculum=10000, starting_rate=None,
                  default_rate=None, variant="image_translation", seed=None, nets=None, process_group=None,
-                 use_graphs=None, data_parallel=True):
+                 use_graphs=None, data_parallel=True, deterministic=False):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("DiscoGANTrainer runs on CUDA (sm_100a) only")
@@ -290,7 +350,12 @@ class DiscoGANTrainer:
         # launch context of this trainer: lanes, scratch buffers and split-K workspaces are its own, so several trainers
         # (or host threads) in one process never share mutable state
         self.ctx = ops.OpsContext()
-        if os.environ.get("DISCOGAN_B200_SPLITK", "1") != "0":
+        # deterministic=True: bit-reproducible iterations (no split-K atomics, BatchNorm statistics in a separate ordered
+        # pass instead of the conv epilogue's shared-memory atomics); a few percent slower at 64x64
+        self.deterministic = deterministic
+        if deterministic:
+            self.ctx.fuse_stats = False
+        if os.environ.get("DISCOGAN_B200_SPLITK", "1") != "0" and not deterministic:
             with ops.use_context(self.ctx):
                 ops.enable_splitk(self.device)
         self.image_size = image_size
@@ -617,13 +682,64 @@ class DiscoGANTrainer:
         return dict(zip(LOSS_NAMES, self.loss_buf.tolist()))
 
     def log_line(self, total_iterations):
-        """The reference's log format (image_translation.py:394-398; parsed by hyperparameter_search.py:269-271)."""
-        l = self.losses()
-        return (f"Iter [{self.iters - 1}/{total_iterations}] "
-                f"GEN: {l['gen_loss_A']:.4f}/{l['gen_loss_B']:.4f}, "
-                f"FM: {l['fm_loss_A']:.4f}/{l['fm_loss_B']:.4f}, "
-                f"RECON: {l['recon_loss_A']:.4f}/{l['recon_loss_B']:.4f}, "
-                f"DIS: {l['dis_loss_A']:.4f}/{l['dis_loss_B']:.4f}")
+        """The reference's log format for the iteration just done (blocking; the CLI uses ``LossReadback`` instead)."""
+        return format_log_line(self.iters - 1, total_iterations, self.losses())
+
+    # ------------------------------------------------------------------------------------------
+    # training state beyond the four state-dicts (SURVEY.md N2): the reference saves weights only
+    # (image_translation.py:420-432) and restarts Adam and the GAN curriculum on --load_*
+    # (distributed_image_translation.py:379-393); this is the part that makes a restart continue instead.
+    def training_state(self):
+        """Iteration counter + per-network Adam moments and step state, CPU tensors keyed like the checkpoints
+        (gen_A / gen_B / dis_A / dis_B)."""
+        st = {"iters": self.iters, "format": 1, "image_size": self.image_size, "model_arch": self.model_arch}
+        for name, net in zip(("gen_A", "gen_B", "dis_A", "dis_B"), self.nets()):
+            f = self.flat[net]
+            st[name] = {"exp_avg": f.exp_avg.detach().cpu().clone(), "exp_avg_sq": f.exp_avg_sq.detach().cpu().clone(),
+                        "adam_state": f.adam_state.detach().cpu().clone()}
+        return st
+
+    def load_training_state(self, st):
+        if st.get("image_size", self.image_size) != self.image_size:
+            raise ValueError(f"training state is for image_size {st.get('image_size')}, trainer is {self.image_size}")
+        for name, net in zip(("gen_A", "gen_B", "dis_A", "dis_B"), self.nets()):
+            f, src = self.flat[net], st[name]
+            if src["exp_avg"].numel() != f.exp_avg.numel():
+                raise ValueError(f"training state of {name} has {src['exp_avg'].numel()} elements, expected {f.exp_avg.numel()}")
+            f.exp_avg.copy_(src["exp_avg"])
+            f.exp_avg_sq.copy_(src["exp_avg_sq"])
+            f.adam_state.copy_(src["adam_state"])
+        self.iters = int(st["iters"])
+
+    def load_weights(self, state_dicts):
+        """Load the four reference-format state-dicts (gen_A, gen_B, dis_A, dis_B order or a dict by those names) into the
+        flat buffers and refresh the bf16 GEMM copies."""
+        if isinstance(state_dicts, dict):
+            state_dicts = [state_dicts.get(k) for k in ("gen_A", "gen_B", "dis_A", "dis_B")]
+        for net, sd in zip(self.nets(), state_dicts):
+            if sd is not None:
+                net.load_state_dict(sd)
+                net._packed.invalidate()
+
+    @torch.no_grad()
+    def sample_images(self, test_A, test_B, mode="reference"):
+        """The four generator passes of ``save_sample_images`` (image_translation.py:170-176): AB, BA, ABA, BAB.
+        mode='reference': like the reference, the generators stay in train mode under no_grad, so the passes use the test
+        batch's statistics AND advance the BatchNorm running statistics / counters.
+        mode='eval': clean eval-mode passes that leave the training state untouched."""
+        if mode not in ("reference", "eval"):
+            raise ValueError(mode)
+        with ops.use_context(self.ctx):
+            if mode == "eval":
+                self.G_A.eval(); self.G_B.eval()
+            try:
+                AB = self.G_B(test_A)
+                BA = self.G_A(test_B)
+                ABA = self.G_A(AB)
+                BAB = self.G_B(BA)
+            finally:
+                self.G_A.train(); self.G_B.train()
+        return AB, BA, ABA, BAB
 
     def nets(self):
         return self.G_A, self.G_B, self.D_A, self.D_B
