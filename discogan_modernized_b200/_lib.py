@@ -15,7 +15,7 @@ PKG_DIR = Path(__file__).resolve().parent
 ROOT = PKG_DIR.parent
 HEADER = ROOT / "include" / "discogan_b200.h"
 LIB_PATH = PKG_DIR / "libdiscogan_b200.so"
-SOURCES = [PKG_DIR / "csrc" / n for n in ("gemm_tc.cu", "c3_tc.cu", "glue.cu", "direct.cu")]
+SOURCES = [PKG_DIR / "csrc" / n for n in ("gemm_tc.cu", "c3_tc.cu", "glue.cu", "direct.cu", "preprocess.cu")]
 
 _CTYPES = {
     "int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,

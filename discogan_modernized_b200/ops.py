@@ -547,6 +547,22 @@ def fm_bwd(diff, B, shape, g):
     return dfeat
 
 
+# ---- input pipeline ---------------------------------------------------------------------------
+def preprocess_u8(table, image_size, out=None):
+    """table: device int64 [n,8] rows {src ptr, H, W, x0, crop_w, mode, 0, 0} (decoded uint8 HWC images in device memory)
+    -> fp32 [n,3,S,S] in [0,1]: crop + (mode 1: 3x3 edge thickening) + bilinear resize + /255 + CHW, cv2-exact."""
+    n = table.shape[0]
+    if table.dim() != 2 or table.shape[1] != 8:
+        raise ValueError(f"table must be [n,8] int64, got {tuple(table.shape)}")
+    if out is None:
+        out = torch.empty(n, 3, image_size, image_size, dtype=F32, device=table.device)
+    elif tuple(out.shape) != (n, 3, image_size, image_size):
+        raise ValueError(f"out shape {tuple(out.shape)} != {(n, 3, image_size, image_size)}")
+    check(lib().dg_preprocess_u8(_ptr(table, torch.int64, "table"), n, image_size, _ptr(out, F32, "out"), _stream()),
+          "dg_preprocess_u8")
+    return out
+
+
 # ---- optimiser --------------------------------------------------------------------------------
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale=1.0):
     """One torch.optim.Adam-equivalent step on flat buffers; `state` = device fp32[4] (zero-initialised once; holds

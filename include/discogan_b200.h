@@ -165,6 +165,15 @@ int dg_fm_bwd(const float* diff, int B, long long n, float g, void* dfeat, dg_st
 int dg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                  float eps, float weight_decay, float* state, float grad_scale, dg_stream_t stream);
 
+/* ---- input pipeline: read_images / DiscoGANDataset._load_and_process_image, dataset.py:37-73,238-261 ----
+ * One launch preprocesses a batch of decoded uint8 RGB images resident in device memory into the trainer's input layout:
+ * out = float [n][3][S][S] in [0,1].  table = device int64 [n][8] rows {src pointer (uint8 [H][W][3]), H, W, x0, crop_w,
+ * mode, 0, 0}: columns [x0, x0+crop_w) are used (the reference crops halves of side-by-side pairs: domain 'A' = columns
+ * [0,256), 'B' = [256,W)); mode 0 = cv2.resize(INTER_LINEAR) of the uint8 image, mode 1 = the domain-'A' edge-map
+ * thickening (255-x, 3x3 dilate, 255-x, in float64) followed by cv2.resize on float64.  Bit-exact with the reference's
+ * cv2 arithmetic in both modes (tests/test_dataset_gpu.py). */
+int dg_preprocess_u8(const long long* table, int n, int S, float* out, dg_stream_t stream);
+
 /* ---- debug-only SIMT versions of the tensor-core convolutions (never the product path) ---- */
 int dg_simt_conv4x4s2_fprop(const void* x, const void* wd, void* z, int B, int H, int W, int Cb, int Cs,
                             dg_stream_t stream);
