@@ -1,10 +1,11 @@
 """Shared command-line plumbing for the re-hosted reference entry points.
 
 Flags and defaults follow the reference parsers (image_translation.py:21-81, angle_pairing.py:22-72,
-distributed_image_translation.py:48-126).  Data: the dataset pipeline (dataset.py) is outside
-the hot path this repo rebuilds, so batches are either synthetic (``--synthetic``, the default when the task's
-folders are absent; precedent batch_size_optimization.py:62-63) or read from two flat image folders
-(``--data_A DIR --data_B DIR``, resized to --image_size, scaled to [0,1], CHW).
+distributed_image_translation.py:48-126).  Data: image files are
+decoded once and kept in HBM, preprocessed per batch by one CUDA launch (``dataset.py`` of this package), so batches
+are either synthetic (``--synthetic``, the default when no folders are given; precedent
+batch_size_optimization.py:62-63) or read from two image folders (``--data_A DIR --data_B DIR``) with the reference's
+read_images semantics (crop halves, edge thickening, bilinear resize, /255, CHW).
 """
 import argparse
 import sys
@@ -59,51 +60,74 @@ def build_parser(kind):
     p.add_argument("--n_samples", type=int, default=5, help="rows of the sample grid (reference: 5)")
     p.add_argument("--deterministic", action="store_true", help="bit-reproducible iterations (slightly slower)")
     p.add_argument("--synthetic", action="store_true", help="uniform-random A/B batches")
-    p.add_argument("--data_A", default=None)
-    p.add_argument("--data_B", default=None)
+    p.add_argument("--data_A", default=None, help="folder of domain-A images (.jpg/.png)")
+    p.add_argument("--data_B", default=None, help="folder of domain-B images")
+    p.add_argument("--domain_A_type", default="auto", choices=["auto", "A", "B", "none"],
+                   help="read_images domain handling for A: 'A' = left half of a side-by-side pair + edge thickening, "
+                        "'B' = right half, 'none' = whole image; auto = by task name as in the reference")
+    p.add_argument("--domain_B_type", default="auto", choices=["auto", "A", "B", "none"])
     p.add_argument("--iters_per_epoch", type=int, default=100, help="synthetic data only")
     p.add_argument("--max_iters", type=int, default=None)
     return p
 
 
-def load_folder(path, size):
-    from PIL import Image
-    import numpy as np
-    files = sorted(list(Path(path).glob("*.jpg")) + list(Path(path).glob("*.png")))
-    if not files:
-        raise FileNotFoundError(f"no .jpg/.png images under {path}")
-    out = []
-    for f in files:
-        im = Image.open(f).convert("RGB").resize((size, size))
-        out.append(torch.from_numpy(np.asarray(im).copy()).permute(2, 0, 1).float() / 255.0)
-    return torch.stack(out)
-
-
 class Batches:
-    """Per-epoch A/B batches; shuffles A and B independently like dataset.shuffle_data (dataset.py:24-35)."""
+    """Per-epoch A/B device batches.
+    Folders (``--data_A DIR --data_B DIR``): ``dataset.DiscoGANDataset`` -- files decoded once into HBM, each batch one
+    preprocessing launch with the reference's read_images arithmetic; domain types follow the task name
+    (image_translation.py:243-251) unless --domain_A_type/--domain_B_type say otherwise.  The single-device entry points
+    shuffle the two domains independently and drop the ragged tail like image_translation.py:296,309-319; the distributed
+    one pairs index i of A with index i of B under the DistributedSampler index stream (distributed_...:182-226).
+    Synthetic (``--synthetic`` or no folders): uniform-random batches (batch_size_optimization.py:62-63)."""
 
-    def __init__(self, args, rank=0, world=1):
-        self.bs, self.S, self.rank, self.world = args.batch_size, args.image_size, rank, world
+    def __init__(self, args, rank=0, world=1, kind="image_translation", device="cuda"):
+        self.bs, self.S, self.rank, self.world, self.kind = args.batch_size, args.image_size, rank, world, kind
+        self.device = device
+        self.A = self.B = None
+        self.ds = None
         if args.data_A and args.data_B and not args.synthetic:
-            self.A, self.B = load_folder(args.data_A, self.S), load_folder(args.data_B, self.S)
-            n = min(len(self.A), len(self.B)) // world
-            self.A, self.B = self.A[rank * n:(rank + 1) * n].pin_memory(), self.B[rank * n:(rank + 1) * n].pin_memory()
-            self.n_batches = n // self.bs
+            from . import dataset
+            da, db = dataset.task_domains(args.task_name)
+            da = args.domain_A_type if args.domain_A_type != "auto" else da
+            db = args.domain_B_type if args.domain_B_type != "auto" else db
+            fa, fb = dataset.list_images(args.data_A), dataset.list_images(args.data_B)
+            n_test = min(args.n_test, len(fa) // 5, len(fb) // 5)          # held-out tail (dataset.py:113-116,165-168)
+            self.test_files = (fa[len(fa) - n_test:], fb[len(fb) - n_test:], da, db) if n_test else None
+            fa, fb = fa[:len(fa) - n_test], fb[:len(fb) - n_test]
+            self.ds = dataset.DiscoGANDataset(fa, fb, {"none": None}.get(da, da), {"none": None}.get(db, db), self.S,
+                                              device=device)
+            if kind == "distributed":
+                self.n_batches = -(-(-(-len(self.ds) // world)) // self.bs)
+            else:
+                self.n_batches = min(len(fa), len(fb)) // self.bs            # image_translation.py:296
+            if self.n_batches == 0:
+                raise ValueError(f"fewer images ({len(fa)}, {len(fb)}) than one batch of {self.bs}")
         else:
-            self.A = self.B = None
+            self.test_files = None
             self.n_batches = args.iters_per_epoch
 
+    def test_tensors(self, n):
+        """The fixed test batch of the sample dumps (image_translation.py:236-252)."""
+        if self.ds is not None and self.test_files:
+            from . import dataset
+            fa, fb, da, db = self.test_files
+            return (dataset.read_images(fa[:n], {"none": None}.get(da, da), self.S, self.device),
+                    dataset.read_images(fb[:n], {"none": None}.get(db, db), self.S, self.device))
+        g = torch.Generator().manual_seed(4321)
+        return (torch.rand(n, 3, self.S, self.S, generator=g).to(self.device),
+                torch.rand(n, 3, self.S, self.S, generator=g).to(self.device))
+
     def epoch(self, epoch):
+        if self.ds is not None:
+            if self.kind == "distributed":
+                yield from self.ds.batches(self.bs, epoch=epoch, rank=self.rank, world=self.world)
+            else:
+                yield from self.ds.batches(self.bs, epoch=epoch, independent=True, drop_last=True)
+            return
         g = torch.Generator().manual_seed(1000 * self.rank + epoch)
-        if self.A is None:
-            for _ in range(self.n_batches):
-                yield (torch.rand(self.bs, 3, self.S, self.S, generator=g).pin_memory(),
-                       torch.rand(self.bs, 3, self.S, self.S, generator=g).pin_memory())
-        else:
-            ia, ib = torch.randperm(len(self.A), generator=g), torch.randperm(len(self.B), generator=g)
-            for i in range(self.n_batches):
-                sl = slice(i * self.bs, (i + 1) * self.bs)
-                yield self.A[ia[sl]].pin_memory(), self.B[ib[sl]].pin_memory()
+        for _ in range(self.n_batches):
+            yield (torch.rand(self.bs, 3, self.S, self.S, generator=g).pin_memory().to(self.device, non_blocking=True),
+                   torch.rand(self.bs, 3, self.S, self.S, generator=g).pin_memory().to(self.device, non_blocking=True))
 
 
 def save_models(tr, model_path, tag):
@@ -146,16 +170,8 @@ def warn_ignored(args):
 
 
 def test_batches(args, data, device):
-    """The fixed test tensors of the sample dumps (image_translation.py:236-252: n_test held-out images per domain;
-    distributed: 10, :369)."""
-    n = max(args.n_samples, 2)                           # train-mode BatchNorm over a 1x1 map needs >= 2 images
-    if data.A is not None:
-        A, B = data.A[-n:], data.B[-n:]
-    else:
-        g = torch.Generator().manual_seed(4321)
-        A = torch.rand(n, 3, args.image_size, args.image_size, generator=g)
-        B = torch.rand(n, 3, args.image_size, args.image_size, generator=g)
-    return A.to(device), B.to(device)
+    """The fixed test tensors of the sample dumps (image_translation.py:236-252: held-out images per domain)."""
+    return data.test_tensors(max(args.n_samples, 2))     # train-mode BatchNorm over a 1x1 map needs >= 2 images
 
 
 def save_sample_grid(tr, test_A, test_B, save_dir, iteration, n_samples=5, mode="reference"):
@@ -194,7 +210,7 @@ def run_training(args, kind, rank=0, world=1, process_group=None):
     if args.resume:
         path, _, tag = args.resume.partition(":")
         load_models(tr, path, tag or "final")
-    data = Batches(args, rank, world)
+    data = Batches(args, rank, world, kind, device)
     total = args.epochs * data.n_batches
     log = None
     test_A = test_B = None
@@ -217,7 +233,7 @@ def run_training(args, kind, rank=0, world=1, process_group=None):
     for epoch in range(args.epochs):
         for A, B in data.epoch(epoch):
             it = tr.iters
-            tr.step(A.to(device, non_blocking=True), B.to(device, non_blocking=True))
+            tr.step(A, B)
             if rank == 0:
                 if it % args.log_interval == 0:            # image_translation.py:393-398, without stalling the GPU
                     emit(readback.request(it))

@@ -558,6 +558,8 @@ def preprocess_u8(table, image_size, out=None):
         out = torch.empty(n, 3, image_size, image_size, dtype=F32, device=table.device)
     elif tuple(out.shape) != (n, 3, image_size, image_size):
         raise ValueError(f"out shape {tuple(out.shape)} != {(n, 3, image_size, image_size)}")
+    if n == 0:
+        return out
     check(lib().dg_preprocess_u8(_ptr(table, torch.int64, "table"), n, image_size, _ptr(out, F32, "out"), _stream()),
           "dg_preprocess_u8")
     return out

@@ -171,3 +171,34 @@ def test_dp_oracle_semantics_gloo_world2():
         (w0, rm0), (w1, rm1) = out[0], out[1]
     assert torch.allclose(w0, w1, atol=1e-7)            # weights stay synchronised
     assert not torch.equal(rm0, rm1)                    # BatchNorm statistics stay per rank
+
+
+def test_log_line_matches_the_reference_parsers():
+    """The log line is parsed by hyperparameter_search.py:269-271 with these regexes; the iteration prefix is
+    image_translation.py:394."""
+    import re
+    from discogan_modernized_b200.train_step import LOSS_NAMES, format_log_line
+    losses = {k: 0.1 * (i + 1) for i, k in enumerate(LOSS_NAMES)}
+    losses["gen_loss_A"] = 12.34567
+    line = format_log_line(150, 2000, losses)
+    assert line.startswith("Iter [150/2000] GEN: 12.3457/")
+    assert re.findall(r"GEN: (\d+\.\d+)/(\d+\.\d+)", line) == [("12.3457", f"{losses['gen_loss_B']:.4f}")]
+    assert re.findall(r"RECON: (\d+\.\d+)/(\d+\.\d+)", line) == [(f"{losses['recon_loss_A']:.4f}", f"{losses['recon_loss_B']:.4f}")]
+    assert re.findall(r"DIS: (\d+\.\d+)/(\d+\.\d+)", line) == [(f"{losses['dis_loss_A']:.4f}", f"{losses['dis_loss_B']:.4f}")]
+    assert re.findall(r"FM: (\d+\.\d+)/(\d+\.\d+)", line) == [(f"{losses['fm_loss_A']:.4f}", f"{losses['fm_loss_B']:.4f}")]
+
+
+def test_sampler_indices_equal_distributed_sampler():
+    from torch.utils.data.distributed import DistributedSampler
+    from discogan_modernized_b200.dataset import domain_crop, sampler_indices, task_domains
+    for length, world in ((20, 2), (23, 4), (7, 8), (64, 1)):
+        for epoch in (0, 5):
+            for rank in range(world):
+                ref = DistributedSampler(range(length), num_replicas=world, rank=rank, shuffle=True, seed=0)
+                ref.set_epoch(epoch)
+                assert sampler_indices(length, rank, world, epoch).tolist() == list(ref)
+    assert task_domains("edges2shoes") == ("A", "B") and task_domains("handbags2shoes") == ("B", "B")
+    assert task_domains("celebA") == (None, None)
+    assert domain_crop("A", 512) == (0, 256, 1) and domain_crop("B", 512) == (256, 256, 0) and domain_crop(None, 178) == (0, 178, 0)
+    with pytest.raises(ValueError):
+        domain_crop("B", 200)

@@ -109,3 +109,42 @@ def test_family64_step_golden(golden_dir, variant, arch):
             assert log[k] == pytest.approx(v, rel=2e-4, abs=1e-6), (it, k)
     assert torch.allclose(nets[0].state_dict()["encoder.0.weight"].flatten()[:64], g["G_A_enc0"], rtol=1e-4, atol=1e-7)
     assert torch.allclose(nets[3].state_dict()["conv1.weight"].flatten()[:64], g["D_B_conv1"], rtol=1e-4, atol=1e-7)
+
+
+def test_preprocess_restatement_matches_cv2():
+    """The numpy restatement of the reference's image arithmetic (dataset.py:50-66; OpenCV's fixed-point bilinear resize,
+    3x3 dilate) against the reference's own dependency (cv2), bit for bit, on seeded images of the dataset geometries."""
+    import numpy as np
+    from oracle.preprocess import preprocess_cv2, preprocess_restated
+    rng = np.random.default_rng(11)
+    for H, W, dom, S in [(256, 512, "A", 64), (256, 512, "B", 64), (218, 178, None, 64), (256, 512, "A", 128),
+                         (97, 131, None, 128), (300, 300, None, 512), (256, 600, "B", 64), (64, 64, None, 64), (33, 300, "A", 64)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        a, b = preprocess_restated(img, dom, S), preprocess_cv2(img, dom, S)
+        assert a.dtype == b.dtype == np.float32 and a.shape == (3, S, S)
+        assert np.array_equal(a, b), (H, W, dom, S, float(np.abs(a - b).max()))
+
+
+def test_bf16_emulation_is_a_small_perturbation_of_the_oracle():
+    """oracle/bf16_emul.py: same parameters, same losses to ~1e-3, running statistics advance identically; its noise-floor
+    twin differs from it end to end by about as much as it differs from fp32 (the rounding cascade its docstring states)."""
+    import torch
+    from oracle.bf16_emul import emulate
+    from oracle.step import OracleStep, build_nets, synthetic_batch
+    torch.set_num_threads(4)
+    S, B = 32, 8
+    A, Bt = synthetic_batch(B, S)
+    nets = {k: build_nets(S) for k in ("fp32", "e", "e2")}
+    st = {"fp32": OracleStep(nets["fp32"]), "e": OracleStep(emulate(nets["e"])), "e2": OracleStep(emulate(nets["e2"], perturb=1e-6))}
+    logs = {k: s.backward(A, Bt) for k, s in st.items()}
+    for k in ("dis_loss_A", "gen_loss_B", "fm_loss_A", "recon_loss_B"):
+        assert abs(logs["e"][k] - logs["fp32"][k]) <= 0.02 * abs(logs["fp32"][k]) + 2e-3, k
+    assert int(nets["e"][0].encoder[3].num_batches_tracked) == int(nets["fp32"][0].encoder[3].num_batches_tracked) == 2
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    g = {k: nets[k][2].conv2.weight.grad for k in nets}
+    gap, floor = rel(g["e"], g["fp32"]), rel(g["e2"], g["e"])
+    assert 1e-3 < gap < 0.5 and 0.3 * gap < floor < 2.0 * gap, (gap, floor)
+    # the optimiser sees the wrapped net's own parameters
+    before = nets["e"][2].conv2.weight.detach().clone()
+    st["e"].apply()
+    assert not torch.equal(nets["e"][2].conv2.weight, before)
