@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--also-512", type=int, default=1, help="also report a 512^2 B=32-per-GPU measurement (every N)")
     ap.add_argument("--also-steps", type=int, default=12)
     ap.add_argument("--no-inference", action="store_true", help="skip the eval-mode AtoB batch sweep")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the image-file input-pipeline measurement")
     return ap.parse_args()
 
 
@@ -494,6 +495,11 @@ def run_b200(args, S, B):
                 line["inference"] = inference_sweep(torch, local)
             except Exception as e:  # noqa: BLE001
                 line["inference"] = {"error": str(e)[:300]}
+        if not args.no_pipeline:
+            try:
+                line["pipeline"] = pipeline_e2e(torch, S, B, min(steps, 150), local, args.model_arch, DiscoGANTrainer)
+            except Exception as e:  # noqa: BLE001
+                line["pipeline"] = {"error": str(e)[:300]}
         if not args.no_cpu_baseline:
             v, msc, cores, sample, _ = cpu_reference_pairs_per_s(S, B, 3, 1, args.model_arch, budget_s=60.0)
             line["cpu_baseline"] = {"value": v, "unit": "image-pairs/s", "cores": cores, "kind": "port", "sample": sample}
@@ -508,14 +514,78 @@ def run_b200(args, S, B):
         os._exit(0)
 
 
+def pipeline_e2e(torch, S, B, steps, local, arch, DiscoGANTrainer):
+    """The train loop fed from IMAGE FILES through the package's own loader (dataset.DiscoGANDataset): synthetic
+    CelebA-sized JPEGs are written to a temp folder, decoded once into HBM, and every step's batch pair is produced by the
+    preprocessing kernel (read_images arithmetic) right before the step.  `value` = image-pairs/s over `steps` steps with
+    a loss readback per step, resident mode; `streaming` = the same loop when the decoded images are NOT cached (host
+    decode per batch), for contrast."""
+    import tempfile
+    import numpy as np
+    from PIL import Image
+    from discogan_modernized_b200 import dataset
+    n_img = 1024
+    with tempfile.TemporaryDirectory() as tmp:
+        rng = np.random.default_rng(0)
+        base = np.linspace(0, 255, 218 * 178 * 3, dtype=np.float32).reshape(218, 178, 3)
+        for d in ("A", "B"):
+            os.makedirs(os.path.join(tmp, d))
+            for i in range(n_img):
+                img = np.clip(np.roll(base, int(rng.integers(0, 178)), 1) + rng.normal(0, 12, base.shape), 0, 255).astype(np.uint8)
+                Image.fromarray(img).save(os.path.join(tmp, d, f"{i:05d}.jpg"), quality=90)
+        fa, fb = dataset.list_images(os.path.join(tmp, "A")), dataset.list_images(os.path.join(tmp, "B"))
+        out = {"unit": "image-pairs/s", "images_per_domain": n_img, "image_hw": [218, 178], "format": "jpeg"}
+        for mode in ("resident", "streaming"):
+            ds = dataset.DiscoGANDataset(fa, fb, None, None, S, device=f"cuda:{local}", cache_bytes=None if mode == "resident" else 0)
+            t0 = time.perf_counter()
+            ds.load()
+            torch.cuda.synchronize()
+            load_s = time.perf_counter() - t0
+            tr = DiscoGANTrainer(image_size=S, device=f"cuda:{local}", model_arch=arch, seed=1234, data_parallel=False)
+
+            def stream():
+                epoch = 0
+                while True:
+                    yield from ds.batches(B, epoch=epoch, drop_last=True)
+                    epoch += 1
+            it = stream()
+            n_steps = steps if mode == "resident" else min(steps, 24)
+            for _ in range(12):
+                tr.step(*next(it))
+            host_loss = torch.empty(8, dtype=torch.float32).pin_memory()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            s.record()
+            for _ in range(n_steps):
+                tr.step(*next(it))
+                host_loss.copy_(tr.loss_buf, non_blocking=True)
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e)
+            if mode == "resident":
+                out.update({"value": B * n_steps / (ms * 1e-3), "ms_per_step": ms / n_steps, "steps": n_steps,
+                            "mode": "decoded images resident in HBM; per step: index gather + dg_preprocess_u8 x2",
+                            "one_time_decode_and_upload_s": round(load_s, 3),
+                            "resident_bytes": int(ds._stores[0].bytes + ds._stores[1].bytes)})
+            else:
+                out["streaming"] = {"value": B * n_steps / (ms * 1e-3), "ms_per_step": ms / n_steps, "steps": n_steps,
+                                    "mode": f"host decode per batch on {ds.workers} threads, prefetch 3"}
+            tr.close()
+            del tr, ds
+            torch.cuda.empty_cache()
+    return out
+
+
 def inference_sweep(torch, local):
     """BASELINE config 5: eval-mode AtoB generator forward (inference.py:149,168-172 batched) over batch sizes, images
     already on the device; CUDA events around `reps` back-to-back forwards after 3 warm-up calls."""
+    from discogan_modernized_b200.inference import GraphedGenerator
     from discogan_modernized_b200.model import Generator
-    out = {"unit": "images/s", "direction": "AtoB", "mode": "eval (BatchNorm running statistics)", "sizes": {}}
+    out = {"unit": "images/s", "direction": "AtoB", "sizes": {},
+           "mode": "eval (BatchNorm running statistics), CUDA-graph replay per batch size (inference.GraphedGenerator)"}
     for size, batches in ((64, (1, 2, 4, 8, 16, 32, 64, 128, 256)), (512, (1, 2, 4, 8, 16, 32, 64, 128, 256))):
         torch.manual_seed(1234)
-        g = Generator(extra_layers=True, image_size=size).to(f"cuda:{local}").eval()
+        g = GraphedGenerator(Generator(extra_layers=True, image_size=size).to(f"cuda:{local}").eval())
         rows = {}
         with torch.no_grad():
             for bsz in batches:

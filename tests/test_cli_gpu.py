@@ -181,3 +181,34 @@ def test_inference_from_checkpoint(tmp_path):
     one = inference.translate(g, imgs[:1], batch_size=1)                  # batch 1 is legal in eval mode
     assert float((one - want[:1]).abs().max()) < 3e-2
     tr.close()
+
+
+def test_batch_size_tool(tmp_path):
+    """N4: the re-hosted batch_size_optimization.py bisects over full train steps and writes the reference's report keys."""
+    from discogan_modernized_b200 import batch_size_optimization as bso
+    out = tmp_path / "bs.json"
+    res = bso.main(["--min_batch", "8", "--max_batch", "32", "--step", "8", "--image_size", "64", "--output", str(out)])
+    assert out.exists()
+    for k in ("gpu_id", "total_memory_mb", "image_size", "model_arch", "extra_layers", "optimal_batch_size",
+              "safe_batch_size", "safety_margin", "memory_usages"):
+        assert k in res
+    assert res["optimal_batch_size"] == 32 and res["safe_batch_size"] == 24          # 32 * 0.9 -> 28 -> multiple of 8
+    assert all(v > 0 for v in res["memory_usages"].values())
+
+
+def test_graphed_inference_matches_eager():
+    from discogan_modernized_b200 import inference
+    from discogan_modernized_b200.model import Generator
+    torch.manual_seed(3)
+    g = Generator(True, 64).cuda().eval()
+    x = torch.rand(9, 3, 64, 64, device="cuda")
+    with torch.no_grad():
+        want = g(x)
+    gg = inference.GraphedGenerator(g)
+    assert torch.equal(gg(x).clone(), want)
+    assert float((gg(x[:4]).clone() - want[:4]).abs().max()) < 3e-2      # another batch size may pick another split-K plan
+    assert torch.equal(gg(x).clone(), want)                              # the first graph is still valid
+    out = inference.translate(g, x.cpu(), batch_size=4)                  # 4 + 4 + 1: three graphs, outputs cloned
+    assert float((out - want).abs().max()) < 3e-2
+    with pytest.raises(ValueError):
+        inference.GraphedGenerator(Generator(True, 64).cuda())     # train mode

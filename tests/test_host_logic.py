@@ -202,3 +202,31 @@ def test_sampler_indices_equal_distributed_sampler():
     assert domain_crop("A", 512) == (0, 256, 1) and domain_crop("B", 512) == (256, 256, 0) and domain_crop(None, 178) == (0, 178, 0)
     with pytest.raises(ValueError):
         domain_crop("B", 200)
+
+
+def test_hyperparameter_search_host_logic(tmp_path):
+    """Sampling space, trial command and log parsing of the re-hosted search tool (hyperparameter_search.py:47-58,253-292)."""
+    import random
+    from discogan_modernized_b200 import hyperparameter_search as hs
+    from discogan_modernized_b200.train_step import LOSS_NAMES, format_log_line
+    hps = hs.sample_hyperparameters(30, random.Random(1))
+    assert len(hps) == 30 and len({tuple(h.values()) for h in hps}) == 30
+    assert all(h[k] in v for h in hps for k, v in hs.PARAM_RANGES.items())
+    log = tmp_path / "train.log"
+    lines = [format_log_line(i * 50, 500, {k: 0.5 / (i + 1) + 0.01 * j for j, k in enumerate(LOSS_NAMES)}) for i in range(4)]
+    log.write_text("Training started\n" + "\n".join(lines) + "\n")
+    m = hs.extract_metrics(log)
+    last = {k: 0.5 / 4 + 0.01 * j for j, k in enumerate(LOSS_NAMES)}
+    assert m["final_recon_loss_A"] == pytest.approx(last["recon_loss_A"], abs=1e-4)
+    assert m["final_gen_loss_B"] == pytest.approx(last["gen_loss_B"], abs=1e-4)
+    assert m["avg_recon_loss"] == pytest.approx((last["recon_loss_A"] + last["recon_loss_B"]) / 2, abs=1e-4)
+    args = hs.parse_args(["--trials", "2", "--output_dir", str(tmp_path), "--base_epochs", "1"])
+    cmd = hs.trial_command(args, hps[0], tmp_path / "t")
+    assert "discogan_modernized_b200.image_translation" in cmd and "--synthetic" in cmd
+    assert cmd[cmd.index("--learning_rate") + 1] == str(hps[0]["learning_rate"])
+    info = {"log_file": str(log), "_best": float("inf"), "_stale": 0, "_seen": 0}
+    args.early_stopping, args.patience = True, 2
+    assert hs.check_early_stop(args, info) is False and info["_seen"] == 4          # loss improves on every line
+    s = hs.analyze_results([{"trial_id": 0, "hyperparameters": hps[0], "metrics": m},
+                            {"trial_id": 1, "hyperparameters": hps[1], "metrics": {"avg_recon_loss": 0.01}}], tmp_path)
+    assert s["best"]["trial_id"] == 1 and (tmp_path / "summary.json").exists()
