@@ -269,11 +269,11 @@ def measure_roofline(tr, batches, torch, pk):
     recs, calls = [], []
 
     def conv_work(name, a):
-        if name in ("conv_down", "conv_down_stats"):
+        if name in ("conv_down", "conv_down_stats", "conv_down_acc"):
             big, wd = a[0], a[1]
             return "conv_gemm", conv_flops(big.shape[0], big.shape[1] // 2, wd.shape[0], big.shape[3]), \
                 f"down B{big.shape[0]} {big.shape[1]}->{big.shape[1] // 2} {big.shape[3]}->{wd.shape[0]}"
-        if name in ("conv_up", "conv_up_stats"):
+        if name in ("conv_up", "conv_up_stats", "conv_up_acc"):
             small, wu = a[0], a[1]
             return "conv_gemm", conv_flops(small.shape[0], small.shape[1], small.shape[3], wu.shape[0]), \
                 f"up B{small.shape[0]} {small.shape[1]}->{2 * small.shape[1]} {small.shape[3]}->{wu.shape[0]}"
@@ -282,14 +282,15 @@ def measure_roofline(tr, batches, torch, pk):
             f"wgrad B{small.shape[0]} {small.shape[1]} {small.shape[3]}x{big.shape[3]}"
 
     def hbm_work(name, a):
-        if name == "bn_act_fwd":
+        if name in ("bn_act_fwd", "bn_act_fwd_acc"):
             return "bn_act_fwd", 4.0 * a[0].numel(), f"bn_fwd {a[0].shape[0]}x{a[0].shape[1]}"   # read z, write y (bf16)
         if name == "bn_act_bwd":                                   # reduce: dy,z ; dx: dy,z + write dz (bf16)
             return "bn_act_bwd", 10.0 * a[0].numel(), f"bn_bwd {a[0].shape[0]}x{a[0].shape[1]}"
         return "adam", 28.0 * a[0].numel(), ""                     # p,g,m,v read + p,m,v write (fp32); +repack excluded
 
-    names = {n: conv_work for n in ("conv_down", "conv_up", "conv_wgrad", "conv_down_stats", "conv_up_stats")}
-    names.update({n: hbm_work for n in ("bn_act_fwd", "bn_act_bwd", "adam_step")})
+    names = {n: conv_work for n in ("conv_down", "conv_up", "conv_wgrad", "conv_down_stats", "conv_up_stats",
+                                    "conv_down_acc", "conv_up_acc")}
+    names.update({n: hbm_work for n in ("bn_act_fwd", "bn_act_fwd_acc", "bn_act_bwd", "adam_step")})
     orig = {n: getattr(ops, n) for n in names}
 
     def wrap(name, fn, work):
@@ -332,6 +333,7 @@ def measure_roofline(tr, batches, torch, pk):
             continue
         try:
             g = torch.cuda.CUDAGraph()
+            tr.ctx.arena.reset()                  # the replayed launches draw their statistics accumulators afresh
             torch.cuda.synchronize()
             with ops.use_context(tr.ctx), torch.cuda.graph(g):      # the trainer's launch plan (split-K workspaces, lanes)
                 keep = [fn(*a, **k) for _, _, fn, a, k in mine]

@@ -52,6 +52,7 @@ struct ConvGemmParams {
   float mask_slope;
   float* img;         // epilogue "image": 3 real output channels written as fp32 NCHW planes instead of `out`
   int img_sigmoid, img_accumulate;
+  int stat_atomic;    // 1: stat_part is one zero-initialised accumulator row pair [2][N]; CTAs add their sums atomically
   float* stat_part;   // BatchNorm statistics fused in the epilogue: per-CTA partial sums [2][gridDim.x][N] of the fp32
                       // accumulators (sum, sum of squares) over the rows this CTA produced; NULL = off
   int splits, kps;    // split-K: work item = (tile, split); a split covers K-iterations [split*kps, (split+1)*kps)
@@ -420,11 +421,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (p.stat_part) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      float* ps = p.stat_part + (size_t)blockIdx.x * p.N;
-      float* pq = p.stat_part + ((size_t)gridDim.x + blockIdx.x) * p.N;
-      for (int i = threadIdx.x - 64; i < p.N; i += 128) {
-        ps[i] = s_stat[i];
-        pq[i] = s_stat[p.N + i];
+      if (p.stat_atomic) {
+        for (int i = threadIdx.x - 64; i < 2 * p.N; i += 128) atomicAdd(p.stat_part + i, s_stat[i]);
+      } else {
+        float* ps = p.stat_part + (size_t)blockIdx.x * p.N;
+        float* pq = p.stat_part + ((size_t)gridDim.x + blockIdx.x) * p.N;
+        for (int i = threadIdx.x - 64; i < p.N; i += 128) {
+          ps[i] = s_stat[i];
+          pq[i] = s_stat[p.N + i];
+        }
       }
     }
   }
@@ -664,8 +669,13 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
       if (acc == 0) acc_phase ^= 1u;
     }
     if (p.stat_part && ch_ok) {
-      p.stat_part[(size_t)blockIdx.x * p.N + ch] = ssum;
-      p.stat_part[((size_t)gridDim.x + blockIdx.x) * p.N + ch] = ssq;
+      if (p.stat_atomic) {
+        atomicAdd(p.stat_part + ch, ssum);
+        atomicAdd(p.stat_part + p.N + ch, ssq);
+      } else {
+        p.stat_part[(size_t)blockIdx.x * p.N + ch] = ssum;
+        p.stat_part[((size_t)gridDim.x + blockIdx.x) * p.N + ch] = ssq;
+      }
     }
   }
 
@@ -687,6 +697,54 @@ splitk_finish_kernel(const float* __restrict__ ws, bf16* __restrict__ out, long 
     const float4 b = *reinterpret_cast<const float4*>(ws + i * 8 + 4);
     const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(f);
+  }
+}
+
+// split-K finish that also accumulates the BatchNorm sums of the fp32 values it converts: acc[2][N] += {sum, sum of squares}
+// over rows.  Block = (N/8 channel vectors) x (256 / (N/8) rows); a thread keeps its 8 channels, strides over rows.
+__global__ void __launch_bounds__(256)
+splitk_finish_stats_kernel(const float* __restrict__ ws, bf16* __restrict__ out, long long rows, int N,
+                           float* __restrict__ acc) {
+  griddep_launch_dependents();
+  griddep_wait();
+  __shared__ float sh1[256 * 8];
+  __shared__ float sh2[256 * 8];
+  const int cw = N >> 3, rows_iter = 256 / cw;
+  const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
+  const int c = tx * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+  if (ty < rows_iter) {
+    for (long long r = (long long)blockIdx.x * rows_iter + ty; r < rows; r += (long long)gridDim.x * rows_iter) {
+      const float4 a = *reinterpret_cast<const float4*>(ws + r * N + c);
+      const float4 b = *reinterpret_cast<const float4*>(ws + r * N + c + 4);
+      const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      *reinterpret_cast<bf16x8*>(out + r * N + c) = pack8(f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += f[i];
+        s2[i] += f[i] * f[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sh1[threadIdx.x * 8 + i] = s1[i];
+    sh2[threadIdx.x * 8 + i] = s2[i];
+  }
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = 0.f, b = 0.f;
+      for (int r = 0; r < rows_iter; ++r) {
+        a += sh1[(r * cw + tx) * 8 + i];
+        b += sh2[(r * cw + tx) * 8 + i];
+      }
+      atomicAdd(acc + c + i, a);
+      atomicAdd(acc + N + c + i, b);
+    }
   }
 }
 
@@ -1163,7 +1221,8 @@ struct ConvGemmExtras {
   float mask_slope = 0.f;
   float* img = nullptr;  // when set: Cb (mode 1 output channels) is the padded 16 and only 3 planes are written
   int img_sigmoid = 0, img_accumulate = 0;
-  float* stat_part = nullptr;  // [2][grid][N] partial BatchNorm sums
+  float* stat_part = nullptr;  // [2][grid][N] partial BatchNorm sums, or (stat_atomic) [2][N] zero-initialised accumulators
+  int stat_atomic = 0;
   int* grid_out = nullptr;     // plan query: receives the grid size, nothing is launched
 };
 
@@ -1265,6 +1324,7 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   p.img_sigmoid = ex.img_sigmoid;
   p.img_accumulate = ex.img_accumulate;
   p.stat_part = ex.stat_part;
+  p.stat_atomic = ex.stat_atomic;
   // split-K for big GEMMs that would leave most SMs idle (M = B*Hs*Ws small, K = taps*Ck large): partial tiles are
   // accumulated in an fp32 workspace and converted afterwards; such launches cannot fuse the BatchNorm statistics
   p.splits = 1;
@@ -1313,15 +1373,18 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     *ex.grid_out = p.ws ? 0 : grid;   // 0: statistics cannot be fused for this shape (split-K)
     return DG_OK;
   }
+  float* splitk_acc = nullptr;
   if (p.ws) {
-    DG_CHECK_ARG(ex.stat_part == nullptr, "conv gemm: fused statistics requested for a split-K shape");
+    DG_CHECK_ARG(ex.stat_part == nullptr || ex.stat_atomic, "conv gemm: fused statistics requested for a split-K shape");
+    splitk_acc = ex.stat_part;      // accumulator mode: the finish kernel sums the fp32 values it converts
+    p.stat_part = nullptr;
     cudaMemsetAsync(p.ws, 0, ws_need, stream);
   }
   const int stage_bytes = use_swap ? 2 * kATileBytes + N * 128 : kATileBytes + (bn / ncta) * 128;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
-  const int smem_bytes = stages * stage_bytes + 1024 + 256 + (ex.stat_part && !use_swap ? 2 * N * (int)sizeof(float) : 0) +
+  const int smem_bytes = stages * stage_bytes + 1024 + 256 + (p.stat_part && !use_swap ? 2 * N * (int)sizeof(float) : 0) +
                          (use_swap ? 4 * 32 * kSwapTrStride * 4 + 768 : 0);
   DG_CHECK_ARG(smem_bytes <= 227 * 1024, "conv gemm: N=%d too wide for fused statistics", N);
 
@@ -1362,7 +1425,16 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     const long long n8 = (long long)(ws_need / sizeof(float)) / 8;
     long long blocks = (n8 + 255) / 256;
     if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
-    dg_launch(splitk_finish_kernel, dg_cfg((int)blocks, 256, 0, stream), p.ws, p.out, n8);
+    if (splitk_acc) {
+      const long long rows = (long long)B * p.Ho * p.Wo;
+      const int rows_iter = 256 / (N / 8);
+      long long sb = (rows + rows_iter * 4 - 1) / (rows_iter * 4);     // ~4 rows per thread
+      if (sb > 2LL * num_sms()) sb = 2LL * num_sms();
+      if (sb < 1) sb = 1;
+      dg_launch(splitk_finish_stats_kernel, dg_cfg((int)sb, 256, 0, stream), (const float*)p.ws, p.out, rows, N, splitk_acc);
+    } else {
+      dg_launch(splitk_finish_kernel, dg_cfg((int)blocks, 256, 0, stream), p.ws, p.out, n8);
+    }
     DG_CHECK_LAUNCH("splitk_finish_kernel");
   }
   return DG_OK;
@@ -1401,6 +1473,7 @@ static ConvGemmExtras extras_from(const dg_conv_opts* o) {
     ex.splitk_ws_bytes = o->splitk_ws_bytes;
     ex.force_bn = o->block_n;
     ex.force_pair = o->pair;
+    ex.stat_atomic = o->stat_accumulate;
   }
   return ex;
 }
@@ -1414,6 +1487,7 @@ int dg_conv_opts_check(const dg_conv_opts* o) {
   DG_CHECK_ARG(o->pair >= -1 && o->pair <= 1 && o->wgrad_pair >= -1 && o->wgrad_pair <= 1, "conv opts: pair=%d wgrad_pair=%d",
                o->pair, o->wgrad_pair);
   DG_CHECK_ARG(((uintptr_t)o->splitk_ws & 15) == 0, "conv opts: split-K workspace must be 16-byte aligned");
+  DG_CHECK_ARG(o->stat_accumulate == 0 || o->stat_accumulate == 1, "conv opts: stat_accumulate=%d", o->stat_accumulate);
   return DG_OK;
 }
 
@@ -1440,6 +1514,7 @@ int dg_conv_stats_rows(int mode, int B, int Hs, int Ws, int Cs, int Cb, const dg
   if (ex.splitk_ws_bytes && !ex.splitk_ws) ex.splitk_ws = reinterpret_cast<float*>(16);   // plan query without a buffer
   ex.grid_out = &grid;
   if (launch_conv_gemm(mode, (const void*)16, (const void*)16, (void*)16, B, Hs, Ws, Cs, Cb, 0, ex) != DG_OK) return 0;
+  if (grid == 0 && ex.stat_atomic) return 1;   // split-K shape: in accumulator mode the finish kernel produces the sums
   return grid;
 }
 int dg_conv4x4s2_fprop_stats(const void* x, const void* wd, void* z, float* stat_part, int B, int H, int W, int Cb,

@@ -180,6 +180,60 @@ BnGeom bn_geom(long long P, int C, int vec, int sms, int blocks_per_sm = 4) {
   return g;
 }
 
+// "Folded finalize": instead of a separate finalize launch between the reduction and its consumer, reductions add their
+// block sums atomically into one zero-initialised accumulator pair per layer (acc_out), and the consumer derives its
+// per-channel coefficients from those sums in its prologue (acc); the first row-block also publishes what the finalize
+// kernel used to publish (statistics + running statistics, or dgamma / dbeta).  Two launches fewer per BatchNorm layer
+// and pass on the dependency chain of the (latency-bound) 64x64 step.
+struct BnFold {
+  const float* acc;        // consumer: {sum, sum2}[C] (forward) or {sum g', sum g'*xhat}[C] (backward dx); NULL = off
+  float* acc_out;          // reduction: add block sums here instead of writing a partial row; NULL = off
+  const float* gamma;
+  const float* beta;
+  float* stats_out;        // forward consumer: {mean, invstd, scale, shift}[C]
+  float* running_mean;
+  float* running_var;
+  float* dgamma;           // backward consumer
+  float* dbeta;
+  float grad_beta;
+  float eps, momentum;
+  double inv_P, unbias;    // 1/P and P/(P-1)
+};
+
+// forward coefficients of channel c from the accumulated sums (same arithmetic as bn_stats_finalize_kernel)
+__device__ __forceinline__ void bn_fold_fwd(const BnFold& f, int C, int c, bool publish, float* sc, float* sh) {
+  const double m = (double)f.acc[c] * f.inv_P;
+  double var = (double)f.acc[C + c] * f.inv_P - m * m;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)f.eps));
+  const float scv = f.gamma[c] * is;
+  *sc = scv;
+  *sh = f.beta[c] - (float)m * scv;
+  if (publish) {
+    f.stats_out[c] = (float)m;
+    f.stats_out[C + c] = is;
+    f.stats_out[2 * C + c] = scv;
+    f.stats_out[3 * C + c] = *sh;
+    if (f.running_mean) {
+      f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * (float)m;
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)(var * f.unbias);
+    }
+  }
+}
+
+// backward-dx coefficients {gamma*invstd, mean(g'), mean(g'*xhat)} of channel c (bn_bwd_finalize_kernel's arithmetic)
+__device__ __forceinline__ void bn_fold_bwd(const BnFold& f, const float* stats, int C, int c, bool publish, float* k0,
+                                            float* k1, float* k2) {
+  const float sg = f.acc[c], sgx = f.acc[C + c];
+  *k0 = f.gamma[c] * stats[C + c];
+  *k1 = (float)((double)sg * f.inv_P);
+  *k2 = (float)((double)sgx * f.inv_P);
+  if (publish && f.dgamma) {
+    f.dgamma[c] = (f.grad_beta != 0.f ? f.grad_beta * f.dgamma[c] : 0.f) + sgx;
+    f.dbeta[c] = (f.grad_beta != 0.f ? f.grad_beta * f.dbeta[c] : 0.f) + sg;
+  }
+}
+
 template <int VEC>
 __device__ __forceinline__ void load_vec(const bf16* p, float* f) {
   if (VEC == 8) {
@@ -201,7 +255,8 @@ __device__ __forceinline__ void store_vec(bf16* p, const float* f) {
 // Block reduction of VEC*2 per-thread values over the row dimension; result written to part{1,2}[split][C].
 template <int VEC>
 __device__ __forceinline__ void bn_block_reduce_store(float* s1, float* s2, int cw, int rows_iter, int tx, int ty,
-                                                      int c, int C, float* part1, float* part2, int split) {
+                                                      int c, int C, float* part1, float* part2, int split,
+                                                      float* acc_out = nullptr) {
   __shared__ float sh1[256 * VEC];
   __shared__ float sh2[256 * VEC];
 #pragma unroll
@@ -219,8 +274,13 @@ __device__ __forceinline__ void bn_block_reduce_store(float* s1, float* s2, int 
         b += sh2[(r * cw + tx) * VEC + i];
       }
       if (c + i < C) {
-        part1[(size_t)split * C + c + i] = a;
-        part2[(size_t)split * C + c + i] = b;
+        if (acc_out) {
+          atomicAdd(acc_out + c + i, a);
+          atomicAdd(acc_out + C + c + i, b);
+        } else {
+          part1[(size_t)split * C + c + i] = a;
+          part2[(size_t)split * C + c + i] = b;
+        }
       }
     }
   }
@@ -229,7 +289,7 @@ __device__ __forceinline__ void bn_block_reduce_store(float* s1, float* s2, int 
 template <int VEC>
 __global__ void __launch_bounds__(256)
 bn_stats_partial_kernel(const bf16* __restrict__ z, long long P, int C, int cw, int rows_iter, int rows_split,
-                        float* __restrict__ part_sum, float* __restrict__ part_sq) {
+                        float* __restrict__ part_sum, float* __restrict__ part_sq, float* __restrict__ acc_out) {
   griddep_launch_dependents();
   griddep_wait();
   const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
@@ -263,7 +323,7 @@ bn_stats_partial_kernel(const bf16* __restrict__ z, long long P, int C, int cw, 
       }
     }
   }
-  bn_block_reduce_store<VEC>(s1, s2, cw, rows_iter, tx, ty, c, C, part_sum, part_sq, blockIdx.y);
+  bn_block_reduce_store<VEC>(s1, s2, cw, rows_iter, tx, ty, c, C, part_sum, part_sq, blockIdx.y, acc_out);
 }
 
 // mean/invstd + scale/shift for the apply kernel + running statistics (momentum update, unbiased variance).
@@ -341,7 +401,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const bf16* __restrict__ z, bf16* __restrict__ y, long long P, int C, int cw, int rows_iter,
                   int rows_split, const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                  float slope) {
+                  float slope, const BnFold fold) {
   griddep_launch_dependents();
   griddep_wait();
   // same (channel vectors) x (rows) block shape as the reductions: a thread keeps its channels' coefficients in
@@ -350,10 +410,16 @@ bn_act_fwd_kernel(const bf16* __restrict__ z, bf16* __restrict__ y, long long P,
   const int c = (blockIdx.x * cw + tx) * VEC;
   if (c >= C) return;
   float sc[VEC], sh[VEC];
+  if (fold.acc) {
+    const bool publish = blockIdx.y == 0 && ty == 0;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    sc[i] = scale[c + i];
-    sh[i] = shift[c + i];
+    for (int i = 0; i < VEC; ++i) bn_fold_fwd(fold, C, c + i, publish, &sc[i], &sh[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      sc[i] = scale[c + i];
+      sh[i] = shift[c + i];
+    }
   }
   const long long r0 = (long long)blockIdx.y * rows_split;
   const long long r1 = min(P, r0 + rows_split);
@@ -404,7 +470,7 @@ __global__ void __launch_bounds__(256, 2)
 bn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const float* __restrict__ bcast,
                       float coef, long long bcast_rows, const bf16* __restrict__ z, const float* __restrict__ stats,
                       long long P, int C, int cw, int rows_iter, int rows_split, int act, float slope,
-                      float* __restrict__ part_g, float* __restrict__ part_gx) {
+                      float* __restrict__ part_g, float* __restrict__ part_gx, float* __restrict__ acc_out) {
   griddep_launch_dependents();
   griddep_wait();
   const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
@@ -453,7 +519,7 @@ bn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2,
 #pragma unroll
     for (int i = 0; i < VEC; ++i) s2[i] *= stats[C + c + i];   // xhat = (z - mean) * invstd
   }
-  bn_block_reduce_store<VEC>(s1, s2, cw, rows_iter, tx, ty, c, C, part_g, part_gx, blockIdx.y);
+  bn_block_reduce_store<VEC>(s1, s2, cw, rows_iter, tx, ty, c, C, part_g, part_gx, blockIdx.y, acc_out);
 }
 
 // dgamma/dbeta (accumulated into the fp32 grads with `beta_acc`) and the three per-channel dx coefficients
@@ -507,7 +573,7 @@ __global__ void __launch_bounds__(256, 2)
 bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const float* __restrict__ bcast, float coef,
                  long long bcast_rows, const bf16* __restrict__ z, const float* __restrict__ stats,
                  const float* __restrict__ coefs, bf16* __restrict__ dz, long long P, int C, int cw, int rows_iter,
-                 int rows_split, int act, float slope) {
+                 int rows_split, int act, float slope, const BnFold fold) {
   griddep_launch_dependents();
   griddep_wait();
   const int tx = threadIdx.x % cw, ty = threadIdx.x / cw;
@@ -520,8 +586,14 @@ bn_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, cons
     const float mu = stats[c + i], is = stats[C + c + i];
     sc[i] = stats[2 * C + c + i];
     sh[i] = stats[3 * C + c + i];
-    k0[i] = coefs[c + i];
-    const float k1 = coefs[C + c + i], k2 = coefs[2 * C + c + i];
+    float k1, k2;
+    if (fold.acc) {
+      bn_fold_bwd(fold, stats, C, c + i, blockIdx.y == 0 && ty == 0, &k0[i], &k1, &k2);
+    } else {
+      k0[i] = coefs[c + i];
+      k1 = coefs[C + c + i];
+      k2 = coefs[2 * C + c + i];
+    }
     a1[i] = -k0[i] * k2 * is;
     a0[i] = -k0[i] * k1 - a1[i] * mu;
   }
@@ -588,6 +660,7 @@ struct BnStreamParams {
   int tiles_per_block;
   int act;
   float slope;
+  BnFold fold;
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
@@ -630,17 +703,28 @@ bn_stream_kernel(const BnStreamParams p) {
 
   // per-channel constants of this thread's 8 channels
   float sc[8], sh[8], k0[8], a1[8], a0[8], mu[8], s1[8], s2[8];
+  const bool publish = blockIdx.x == 0 && ty == 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    sc[i] = p.stats[2 * C + c + i];
-    sh[i] = p.stats[3 * C + c + i];
     s1[i] = s2[i] = 0.f;
     mu[i] = k0[i] = a1[i] = a0[i] = 0.f;
+    if (MODE == BS_FWD && p.fold.acc) {
+      bn_fold_fwd(p.fold, C, c + i, publish, &sc[i], &sh[i]);
+      continue;
+    }
+    sc[i] = p.stats[2 * C + c + i];
+    sh[i] = p.stats[3 * C + c + i];
     if (MODE == BS_BWD_PARTIAL) mu[i] = p.stats[c + i];
     if (MODE == BS_BWD_DX) {
       const float m = p.stats[c + i], is = p.stats[C + c + i];
-      k0[i] = p.coefs[c + i];
-      const float k1 = p.coefs[C + c + i], k2 = p.coefs[2 * C + c + i];
+      float k1, k2;
+      if (p.fold.acc) {
+        bn_fold_bwd(p.fold, p.stats, C, c + i, publish, &k0[i], &k1, &k2);
+      } else {
+        k0[i] = p.coefs[c + i];
+        k1 = p.coefs[C + c + i];
+        k2 = p.coefs[2 * C + c + i];
+      }
       a1[i] = -k0[i] * k2 * is;                // dz = k0*(g' - k1 - (z-mu)*is*k2) = k0*g' + a1*z + a0
       a0[i] = -k0[i] * k1 - a1[i] * m;
     }
@@ -715,8 +799,13 @@ bn_stream_kernel(const BnStreamParams p) {
           a += sh1[(r * cw + tx) * 8 + k];
           b += sh2[(r * cw + tx) * 8 + k];
         }
-        p.part0[(size_t)blockIdx.x * C + c + k] = a;
-        p.part1[(size_t)blockIdx.x * C + c + k] = b;
+        if (p.fold.acc_out) {
+          atomicAdd(p.fold.acc_out + c + k, a);
+          atomicAdd(p.fold.acc_out + C + c + k, b);
+        } else {
+          p.part0[(size_t)blockIdx.x * C + c + k] = a;
+          p.part1[(size_t)blockIdx.x * C + c + k] = b;
+        }
       }
     }
   }
@@ -1104,9 +1193,11 @@ int dg_bn_stats(const void* z, long long P, int C, const float* gamma, const flo
   float* pq = scratch + (size_t)g.gy * C;
   dim3 grid(g.gx, g.gy);
   if (vec == 8)
-    dg_launch(bn_stats_partial_kernel<8>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq);
+    dg_launch(bn_stats_partial_kernel<8>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq,
+              (float*)nullptr);
   else
-    dg_launch(bn_stats_partial_kernel<1>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq);
+    dg_launch(bn_stats_partial_kernel<1>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split, ps, pq,
+              (float*)nullptr);
   DG_CHECK_LAUNCH("bn_stats_partial");
   dg_launch(bn_stats_finalize_kernel, dg_cfg(dg_ceil_div(C, 32), 256, 0, stream), ps, pq, g.gy, P, C, eps, momentum, gamma, beta,
                                                                     stats, stats + C, stats + 2 * C, stats + 3 * C,
@@ -1138,10 +1229,57 @@ int dg_bn_eval_coeffs(const float* gamma, const float* beta, const float* runnin
   return DG_OK;
 }
 
+// sums of z[P][C] added into the zero-initialised accumulator pair acc[2][C] (folded-finalize producer for layers whose
+// convolution could not fuse the statistics: the 4x4 valid heads)
+int dg_bn_stats_acc(const void* z, long long P, int C, float* acc, cudaStream_t stream) {
+  DG_CHECK_ARG(P > 0 && C > 0 && z && acc, "bn_stats_acc: bad args");
+  const int vec = (C % 8 == 0) ? 8 : 1;
+  BnGeom g = bn_geom(P, C, vec, sms());
+  dim3 grid(g.gx, g.gy);
+  if (vec == 8)
+    dg_launch(bn_stats_partial_kernel<8>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split,
+              (float*)nullptr, (float*)nullptr, acc);
+  else
+    dg_launch(bn_stats_partial_kernel<1>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, P, C, g.cw, g.rows_iter, g.rows_split,
+              (float*)nullptr, (float*)nullptr, acc);
+  DG_CHECK_LAUNCH("bn_stats_partial");
+  return DG_OK;
+}
+
+static int bn_act_fwd_impl(const void* z, void* y, long long P, int C, const float* stats, int act, float slope,
+                           const BnFold& fold, cudaStream_t stream);
+
 // y = act(z * scale + shift)
 int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats, int act, float slope,
                   cudaStream_t stream) {
   DG_CHECK_ARG(P > 0 && C > 0 && z && y && stats, "bn_act_fwd: bad args");
+  BnFold fold = {};
+  return bn_act_fwd_impl(z, y, P, C, stats, act, slope, fold, stream);
+}
+
+// y = act(BN_train(z)) with the statistics taken from accumulated sums acc[2][C] = {sum z, sum z^2} (filled by the
+// producing convolution's epilogue in accumulator mode, or by dg_bn_stats_acc): no finalize launch.  Also writes
+// stats[4][C] = {mean, invstd, scale, shift} for the backward pass and updates the running statistics (may be NULL).
+int dg_bn_act_fwd_acc(const void* z, void* y, long long P, int C, const float* acc, const float* gamma, const float* beta,
+                      float eps, float momentum, float* stats, float* running_mean, float* running_var, int act,
+                      float slope, cudaStream_t stream) {
+  DG_CHECK_ARG(P > 0 && C > 0 && z && y && acc && gamma && beta && stats, "bn_act_fwd_acc: bad args");
+  BnFold fold = {};
+  fold.acc = acc;
+  fold.gamma = gamma;
+  fold.beta = beta;
+  fold.stats_out = stats;
+  fold.running_mean = running_mean;
+  fold.running_var = running_mean ? running_var : nullptr;
+  fold.eps = eps;
+  fold.momentum = momentum;
+  fold.inv_P = 1.0 / (double)P;
+  fold.unbias = P > 1 ? (double)P / (double)(P - 1) : 1.0;
+  return bn_act_fwd_impl(z, y, P, C, stats, act, slope, fold, stream);
+}
+
+static int bn_act_fwd_impl(const void* z, void* y, long long P, int C, const float* stats, int act, float slope,
+                           const BnFold& fold, cudaStream_t stream) {
   BnStreamPlan pl;
   if (((uintptr_t)z & 15) == 0 && ((uintptr_t)y & 15) == 0 && bn_stream_plan(P, C, 1, sms(), &pl)) {
     BnStreamParams sp = {};
@@ -1156,6 +1294,7 @@ int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats
     sp.tiles_per_block = pl.tiles_per_block;
     sp.act = act;
     sp.slope = slope;
+    sp.fold = fold;
     return bn_stream_launch<BS_FWD>(sp, pl, stream);
   }
   const int vec = (C % 8 == 0) ? 8 : 1;
@@ -1163,16 +1302,21 @@ int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats
   dim3 grid(g.gx, g.gy);
   if (vec == 8)
     dg_launch(bn_act_fwd_kernel<8>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, (bf16*)y, P, C, g.cw, g.rows_iter, g.rows_split,
-                                                   stats + 2 * C, stats + 3 * C, act, slope);
+                                                   stats + 2 * C, stats + 3 * C, act, slope, fold);
   else
     dg_launch(bn_act_fwd_kernel<1>, dg_cfg(grid, 256, 0, stream), (const bf16*)z, (bf16*)y, P, C, g.cw, g.rows_iter, g.rows_split,
-                                                   stats + 2 * C, stats + 3 * C, act, slope);
+                                                   stats + 2 * C, stats + 3 * C, act, slope, fold);
   DG_CHECK_LAUNCH("bn_act_fwd");
   return DG_OK;
 }
 
 // Backward of y = act(BN_train(z)).  Upstream gradient g = dy (+ dy2) (+ bcast_coef * bcast[row % bcast_rows]).
 // dgamma/dbeta: fp32 grads, new = grad_beta*old + value (grad_beta 0 overwrites).  coefs: float[3*C] scratch.
+static int bn_act_bwd_impl(const void* dy, const void* dy2, const float* bcast, float bcast_coef, long long bcast_rows,
+                           const void* z, const float* stats, const float* gamma, long long P, int C, int act,
+                           float slope, float* dgamma, float* dbeta, float grad_beta, void* dz, float* coefs,
+                           float* scratch, float* acc2, cudaStream_t stream);
+
 int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bcast_coef, long long bcast_rows,
                   const void* y, const void* z, const float* stats, const float* gamma, long long P, int C, int act,
                   float slope, float* dgamma, float* dbeta, float grad_beta, void* dz, float* coefs, float* scratch,
@@ -1180,6 +1324,34 @@ int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bca
   (void)y;  // the activation derivative is recomputed from z and the statistics; y is accepted for API symmetry
   DG_CHECK_ARG(P > 0 && C > 0 && dy && z && stats && dz && coefs && scratch, "bn_act_bwd: bad args");
   DG_CHECK_ARG(!bcast || bcast_rows > 0, "bn_act_bwd: bcast_rows must be positive");
+  return bn_act_bwd_impl(dy, dy2, bcast, bcast_coef, bcast_rows, z, stats, gamma, P, C, act, slope, dgamma, dbeta, grad_beta,
+                         dz, coefs, scratch, nullptr, stream);
+}
+
+// Same backward in two launches instead of three: the reduction adds {sum g', sum g'*xhat} into the zero-initialised
+// accumulator pair acc2[2][C], the dx kernel derives its coefficients from it and writes dgamma / dbeta.
+int dg_bn_act_bwd_acc(const void* dy, const void* dy2, const float* bcast, float bcast_coef, long long bcast_rows,
+                      const void* z, const float* stats, const float* gamma, long long P, int C, int act, float slope,
+                      float* dgamma, float* dbeta, float grad_beta, void* dz, float* acc2, cudaStream_t stream) {
+  DG_CHECK_ARG(P > 0 && C > 0 && dy && z && stats && dz && acc2 && gamma, "bn_act_bwd_acc: bad args");
+  DG_CHECK_ARG(!bcast || bcast_rows > 0, "bn_act_bwd_acc: bcast_rows must be positive");
+  DG_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "bn_act_bwd_acc: dgamma and dbeta go together");
+  return bn_act_bwd_impl(dy, dy2, bcast, bcast_coef, bcast_rows, z, stats, gamma, P, C, act, slope, dgamma, dbeta, grad_beta,
+                         dz, nullptr, nullptr, acc2, stream);
+}
+
+static int bn_act_bwd_impl(const void* dy, const void* dy2, const float* bcast, float bcast_coef, long long bcast_rows,
+                           const void* z, const float* stats, const float* gamma, long long P, int C, int act,
+                           float slope, float* dgamma, float* dbeta, float grad_beta, void* dz, float* coefs,
+                           float* scratch, float* acc2, cudaStream_t stream) {
+  BnFold fold = {};
+  if (acc2) {
+    fold.gamma = gamma;
+    fold.dgamma = dgamma;
+    fold.dbeta = dbeta;
+    fold.grad_beta = grad_beta;
+    fold.inv_P = 1.0 / (double)P;
+  }
   BnStreamPlan pl;
   if ((((uintptr_t)dy | (uintptr_t)dy2 | (uintptr_t)z | (uintptr_t)dz | (uintptr_t)bcast) & 15) == 0 &&
       bn_stream_plan(P, C, dy2 ? 3 : 2, sms(), &pl)) {
@@ -1194,7 +1366,7 @@ int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bca
     sp.stats = stats;
     sp.coefs = coefs;
     sp.part0 = scratch;
-    sp.part1 = scratch + (size_t)pl.grid * C;
+    sp.part1 = scratch ? scratch + (size_t)pl.grid * C : nullptr;
     sp.P = P;
     sp.C = C;
     sp.rows_tile = pl.rows_tile;
@@ -1202,42 +1374,52 @@ int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bca
     sp.tiles_per_block = pl.tiles_per_block;
     sp.act = act;
     sp.slope = slope;
+    sp.fold = fold;
+    sp.fold.acc_out = acc2;
     int rc = bn_stream_launch<BS_BWD_PARTIAL>(sp, pl, stream);
     if (rc) return rc;
-    dg_launch(bn_bwd_finalize_kernel, dg_cfg(dg_ceil_div(C, 32), 256, 0, stream), (const float*)sp.part0,
-              (const float*)sp.part1, pl.grid, P, C, gamma, stats + C, dgamma, dbeta, grad_beta, coefs);
-    DG_CHECK_LAUNCH("bn_bwd_finalize");
+    if (!acc2) {
+      dg_launch(bn_bwd_finalize_kernel, dg_cfg(dg_ceil_div(C, 32), 256, 0, stream), (const float*)sp.part0,
+                (const float*)sp.part1, pl.grid, P, C, gamma, stats + C, dgamma, dbeta, grad_beta, coefs);
+      DG_CHECK_LAUNCH("bn_bwd_finalize");
+    }
+    sp.fold.acc_out = nullptr;
+    sp.fold.acc = acc2;
     sp.out = (bf16*)dz;
     return bn_stream_launch<BS_BWD_DX>(sp, pl, stream);
   }
   const int vec = (C % 8 == 0) ? 8 : 1;
   BnGeom g = bn_geom(P, C, vec, sms());
   float* pg = scratch;
-  float* pgx = scratch + (size_t)g.gy * C;
+  float* pgx = scratch ? scratch + (size_t)g.gy * C : nullptr;
   dim3 grid(g.gx, g.gy);
   const float* invstd = stats + C;
+  BnFold fold_dx = fold;
+  fold_dx.acc = acc2;
   if (vec == 8)
     dg_launch(bn_bwd_partial_kernel<8>, dg_cfg(grid, 256, 0, stream), (const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
                                                        (const bf16*)z, stats, P, C, g.cw, g.rows_iter, g.rows_split, act,
-                                                       slope, pg, pgx);
+                                                       slope, pg, pgx, acc2);
   else
     dg_launch(bn_bwd_partial_kernel<1>, dg_cfg(grid, 256, 0, stream), (const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
                                                        (const bf16*)z, stats, P, C, g.cw, g.rows_iter, g.rows_split, act,
-                                                       slope, pg, pgx);
+                                                       slope, pg, pgx, acc2);
   DG_CHECK_LAUNCH("bn_bwd_partial");
-  dg_launch(bn_bwd_finalize_kernel, dg_cfg(dg_ceil_div(C, 32), 256, 0, stream), pg, pgx, g.gy, P, C, gamma, invstd, dgamma, dbeta,
-                                                                 grad_beta, coefs);
-  DG_CHECK_LAUNCH("bn_bwd_finalize");
+  if (!acc2) {
+    dg_launch(bn_bwd_finalize_kernel, dg_cfg(dg_ceil_div(C, 32), 256, 0, stream), pg, pgx, g.gy, P, C, gamma, invstd, dgamma, dbeta,
+                                                                   grad_beta, coefs);
+    DG_CHECK_LAUNCH("bn_bwd_finalize");
+  }
   BnGeom g2 = bn_geom(P, C, vec, sms(), 8);
   dim3 grid2(g2.gx, g2.gy);
   if (vec == 8)
     dg_launch(bn_bwd_dx_kernel<8>, dg_cfg(grid2, 256, 0, stream), (const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
                                                    (const bf16*)z, stats, coefs, (bf16*)dz, P, C, g2.cw, g2.rows_iter,
-                                                   g2.rows_split, act, slope);
+                                                   g2.rows_split, act, slope, fold_dx);
   else
     dg_launch(bn_bwd_dx_kernel<1>, dg_cfg(grid2, 256, 0, stream), (const bf16*)dy, (const bf16*)dy2, bcast, bcast_coef, bcast_rows,
                                                    (const bf16*)z, stats, coefs, (bf16*)dz, P, C, g2.cw, g2.rows_iter,
-                                                   g2.rows_split, act, slope);
+                                                   g2.rows_split, act, slope, fold_dx);
   DG_CHECK_LAUNCH("bn_bwd_dx");
   return DG_OK;
 }

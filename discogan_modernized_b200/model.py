@@ -143,8 +143,12 @@ def _bump_counters(mod, training):
 
 
 def _conv_bn(conv_fn, conv_stats_fn, x, w, training):
-    """Run a GEMM convolution; in training mode its epilogue also produces the partial BatchNorm sums."""
-    if training and ops._conv_impl == "tc" and ops.current().fuse_stats:
+    """Run a GEMM convolution; in training mode its epilogue also produces the BatchNorm sums: one accumulator pair
+    [2, C] per layer (folded finalize, the default) or per-CTA partial rows [2, rows, C]."""
+    ctx = ops.current()
+    if training and ops._conv_impl == "tc" and ctx.fuse_stats:
+        if ctx.fold_stats:
+            return (ops.conv_down_acc if conv_fn is ops.conv_down else ops.conv_up_acc)(x, w)
         return conv_stats_fn(x, w)
     return conv_fn(x, w), None
 
@@ -159,6 +163,14 @@ def _bn_act(z, bn, act, training, part=None, bump=True):
             raise ValueError("Expected more than 1 value per channel when training")
         rm, rv = (bn.running_mean, bn.running_var) if (training and bn.track_running_stats) else (None, None)
         mom = bn.momentum if bn.momentum is not None else 0.1
+        if ops.current().fold_stats and (part is None or part.dim() == 2):
+            # folded finalize: the consumer derives the coefficients from the accumulated sums (of the conv epilogue, or of
+            # a reduction pass for the 4x4 valid heads)
+            acc = part if part is not None else ops.bn_stats_acc(z2)
+            y, stats = ops.bn_act_fwd_acc(z2, acc, bn.weight.detach(), bn.bias.detach(), act, LRELU_SLOPE, rm, rv, bn.eps, mom)
+            if rm is not None and bump:
+                bn.num_batches_tracked.add_(1)
+            return y.view(z.shape), stats
         if part is not None:
             stats = ops.bn_stats_finalize(part, z2.shape[0], bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, mom)
         else:

@@ -33,6 +33,38 @@ def _ptr(t, dtype=None, name="tensor"):
     return t.data_ptr()
 
 
+class StatArena:
+    """Zero-initialised fp32 accumulators for the folded BatchNorm reductions (``dg_conv_opts.stat_accumulate``,
+    ``dg_bn_act_fwd_acc`` / ``dg_bn_act_bwd_acc``).  ``take(n)`` hands out the next n floats; a trainer calls ``reset()``
+    once per iteration before any lane starts, which rewinds the cursor and re-zeroes what the previous iteration used
+    with ONE memset (captured as the first node of the step graph).  Without resets (eager module calls) the arena simply
+    keeps allocating fresh zeroed chunks."""
+
+    def __init__(self, ctx, floats=1 << 20):
+        self.ctx, self.floats = ctx, floats
+        self.buf, self.cursor, self.high = None, 0, 0
+
+    def take(self, n, device):
+        n = (n + 63) // 64 * 64
+        if self.buf is None or self.buf.device != torch.device(device) or self.cursor + n > self.buf.numel():
+            if torch.cuda.is_current_stream_capturing():
+                raise KernelError("statistics arena would be (re)allocated during CUDA-graph capture; run one eager step first")
+            if self.buf is not None:
+                self.floats = 2 * max(self.floats, n)        # an iteration must fit one buffer (graph capture needs it)
+            self.buf = torch.zeros(max(self.floats, n), dtype=F32, device=device)
+            self.cursor = 0
+            self.ctx.generation += 1
+        out = self.buf[self.cursor:self.cursor + n]
+        self.cursor += n
+        self.high = max(self.high, self.cursor)
+        return out
+
+    def reset(self):
+        if self.buf is not None and self.high:
+            self.buf[:self.high].zero_()
+        self.cursor = 0
+
+
 class OpsContext:
     """Everything the wrappers need beyond their arguments: which lane (stream slot) the caller is on, where weight-
     gradient kernels go, the grow-only scratch buffers and split-K workspaces (per device and lane), and the test-only
@@ -52,9 +84,13 @@ class OpsContext:
         # BatchNorm statistics from the conv epilogue's fp32 accumulators (shared-memory float atomics: the summation
         # order, hence the last bit, varies from run to run); off = a separate deterministic statistics pass
         self.fuse_stats = os.environ.get("DISCOGAN_B200_FUSE_STATS", "1") != "0"
+        # folded finalize: reductions add into arena accumulators, consumers derive their coefficients (two launches
+        # fewer per BatchNorm layer and pass); off = per-CTA partial rows + finalize kernels
+        self.fold_stats = self.fuse_stats and os.environ.get("DISCOGAN_B200_FOLD_STATS", "1") != "0"
+        self.arena = StatArena(self)
         self._opts = {}
 
-    def conv_opts(self, device, splitk=True):
+    def conv_opts(self, device, splitk=True, accumulate=False):
         """ctypes ``dg_conv_opts`` for a launch on the current lane (cached per (device, lane): the struct must stay
         alive until the call returns, and its address is stable for repeated launches)."""
         device = torch.device(device)
@@ -70,12 +106,13 @@ class OpsContext:
                 self.splitk_ws[key] = buf
                 self.generation += 1
             ptr = buf.data_ptr()
-        key = (device, self.lane, bool(nbytes))
+        key = (device, self.lane, bool(nbytes), accumulate)
         o = self._opts.get(key)
         if o is None:
             o = self._opts[key] = ConvOpts()
         o.splitk_ws, o.splitk_ws_bytes = ptr or None, nbytes
         o.block_n, o.pair, o.wgrad_pair = self.block_n, self.pair, self.wgrad_pair
+        o.stat_accumulate = int(accumulate)
         return ctypes.byref(o)
 
     def plan_opts(self, device):
@@ -167,8 +204,8 @@ def enable_splitk(device, nbytes=64 << 20):
     current().splitk_bytes[torch.device(device)] = int(nbytes)
 
 
-def _opts(device, splitk=True):
-    return current().conv_opts(device, splitk)
+def _opts(device, splitk=True, accumulate=False):
+    return current().conv_opts(device, splitk, accumulate)
 
 
 # ---- weights / layout ---------------------------------------------------------------------
@@ -267,6 +304,30 @@ def conv_down_stats(big, wd):
     check(lib().dg_conv4x4s2_fprop_stats(_ptr(big, BF16, "big"), _ptr(wd, BF16, "wd"), _ptr(out), _ptr(part), B, H, W, Cb,
                                          Cs, _opts(big.device), _stream()), "dg_conv4x4s2_fprop_stats")
     return out, part
+
+
+def conv_down_acc(big, wd):
+    """conv_down whose epilogue adds the per-channel sums / sums of squares of its fp32 output into a fresh zeroed arena
+    accumulator: (out, acc fp32 [2, Cs]).  Works for every shape (split-K layers: the finish kernel sums)."""
+    B, H, W, Cb = big.shape
+    Cs = wd.shape[0]
+    out = torch.empty(B, H // 2, W // 2, Cs, dtype=BF16, device=big.device)
+    acc = current().arena.take(2 * Cs, big.device)[:2 * Cs].view(2, Cs)
+    check(lib().dg_conv4x4s2_fprop_stats(_ptr(big, BF16, "big"), _ptr(wd, BF16, "wd"), _ptr(out), acc.data_ptr(), B, H, W, Cb,
+                                         Cs, _opts(big.device, accumulate=True), _stream()), "dg_conv4x4s2_fprop_stats")
+    return out, acc
+
+
+def conv_up_acc(small, wu):
+    """conv_up (ConvTranspose2d forward) with accumulated statistics: (out, acc fp32 [2, Cb])."""
+    B, Hs, Ws, Cs = small.shape
+    Cb = wu.shape[0]
+    out = torch.empty(B, 2 * Hs, 2 * Ws, Cb, dtype=BF16, device=small.device)
+    acc = current().arena.take(2 * Cb, small.device)[:2 * Cb].view(2, Cb)
+    check(lib().dg_convT4x4s2_fprop_stats(_ptr(small, BF16, "small"), _ptr(wu, BF16, "wu"), _ptr(out), acc.data_ptr(), B, Hs,
+                                          Ws, Cs, Cb, _opts(small.device, accumulate=True), _stream()),
+          "dg_convT4x4s2_fprop_stats")
+    return out, acc
 
 
 def conv_up_stats(small, wu):
@@ -444,6 +505,25 @@ def bn_stats_finalize(part, P, gamma, beta, running_mean=None, running_var=None,
     return stats
 
 
+def bn_stats_acc(z2d):
+    """Sums / sums of squares of z[P,C] added into a fresh zeroed arena accumulator -> acc fp32 [2, C]."""
+    P, C = z2d.shape
+    acc = current().arena.take(2 * C, z2d.device)[:2 * C].view(2, C)
+    check(lib().dg_bn_stats_acc(_ptr(z2d, BF16, "z"), P, C, acc.data_ptr(), _stream()), "dg_bn_stats_acc")
+    return acc
+
+
+def bn_act_fwd_acc(z2d, acc, gamma, beta, act, slope=0.2, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
+    """y = act(BN_train(z)) with the statistics derived from acc inside the kernel; returns (y, stats fp32 [4, C])."""
+    P, C = z2d.shape
+    y = torch.empty_like(z2d)
+    stats = torch.empty(4, C, dtype=F32, device=z2d.device)
+    check(lib().dg_bn_act_fwd_acc(_ptr(z2d, BF16, "z"), _ptr(y), P, C, _ptr(acc, F32, "acc"), _ptr(gamma, F32, "gamma"),
+                                  _ptr(beta, F32, "beta"), eps, momentum, _ptr(stats), _ptr(running_mean, F32, "running_mean"),
+                                  _ptr(running_var, F32, "running_var"), act, slope, _stream()), "dg_bn_act_fwd_acc")
+    return y, stats
+
+
 def bn_eval_stats(gamma, beta, running_mean, running_var, eps=1e-5):
     C = gamma.numel()
     stats = torch.zeros(4, C, dtype=F32, device=gamma.device)
@@ -466,11 +546,18 @@ def bn_act_bwd(dy2d, y2d, z2d, stats, gamma, act, slope=0.2, dgamma=None, dbeta=
     grad_beta*old + new when given."""
     P, C = z2d.shape
     dz = torch.empty_like(z2d)
-    coefs = torch.empty(3, C, dtype=F32, device=z2d.device)
-    sc = _bn_scratch(P, C, z2d.device)
     bcast_rows = 0
     if bcast is not None:
         bcast_rows = bcast.numel() // C
+    if current().fold_stats:      # two launches: reduction into an arena accumulator, dx derives its coefficients
+        acc2 = current().arena.take(2 * C, z2d.device)
+        check(lib().dg_bn_act_bwd_acc(_ptr(dy2d, BF16, "dy"), _ptr(dy2, BF16, "dy2"), _ptr(bcast, F32, "bcast"), bcast_coef,
+                                      bcast_rows, _ptr(z2d, BF16, "z"), _ptr(stats, F32, "stats"), _ptr(gamma, F32, "gamma"),
+                                      P, C, act, slope, _ptr(dgamma, F32, "dgamma"), _ptr(dbeta, F32, "dbeta"), grad_beta,
+                                      _ptr(dz), acc2.data_ptr(), _stream()), "dg_bn_act_bwd_acc")
+        return dz
+    coefs = torch.empty(3, C, dtype=F32, device=z2d.device)
+    sc = _bn_scratch(P, C, z2d.device)
     check(lib().dg_bn_act_bwd(_ptr(dy2d, BF16, "dy"), _ptr(dy2, BF16, "dy2"), _ptr(bcast, F32, "bcast"), bcast_coef, bcast_rows,
                               _ptr(y2d, BF16, "y"), _ptr(z2d, BF16, "z"), _ptr(stats, F32, "stats"), _ptr(gamma, F32, "gamma"),
                               P, C, act, slope, _ptr(dgamma, F32, "dgamma"), _ptr(dbeta, F32, "dbeta"), grad_beta, _ptr(dz),

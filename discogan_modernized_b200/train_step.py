@@ -354,7 +354,7 @@ class DiscoGANTrainer:
         # pass instead of the conv epilogue's shared-memory atomics); a few percent slower at 64x64
         self.deterministic = deterministic
         if deterministic:
-            self.ctx.fuse_stats = False
+            self.ctx.fuse_stats = self.ctx.fold_stats = False
         if os.environ.get("DISCOGAN_B200_SPLITK", "1") != "0" and not deterministic:
             with ops.use_context(self.ctx):
                 ops.enable_splitk(self.device)
@@ -532,6 +532,7 @@ class DiscoGANTrainer:
         networks; with ``reduce`` their flat gradients are handed to the data-parallel reducer as they complete."""
         co = loss_coefficients(self.model_arch, rate)
         G_A, G_B, D_A, D_B = self.G_A, self.G_B, self.D_A, self.D_B
+        self.ctx.arena.reset()        # one memset re-zeroes every BatchNorm accumulator of the iteration (before the lanes fork)
         save_g = not is_dis
         lane, fork, join = self._lane, self._fork, self._join
         # forward, phase 1 (4 lanes): the two first generator passes and the two real discriminator passes

@@ -55,6 +55,10 @@ int dg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int HW, int C, dg_s
  *             output channels wherever it is eligible)
  *   pair      test hook: CTA pairs (tcgen05 cta_group::2, two M tiles per MMA): 1/0, -1 = default (on)
  *   wgrad_pair  same for the weight-gradient kernel (cta_group::2 pair kernel vs multicast cluster kernel)
+ *   stat_accumulate  the *_stats entry points: 0 = stat_part receives one row of partial sums per CTA (finish with
+ *             dg_bn_stats_finalize); 1 = stat_part is ONE zero-initialised accumulator pair float[2][N] that every CTA
+ *             adds its sums to (red.global.add) -- consumed directly by dg_bn_act_fwd_acc, no finalize launch; split-K
+ *             shapes are supported in this mode (the split-K finish kernel produces the sums)
  * Results do not depend on block_n / pair / wgrad_pair (bit-identical except for split-K summation order). */
 typedef struct dg_conv_opts {
   void* splitk_ws;
@@ -62,6 +66,7 @@ typedef struct dg_conv_opts {
   int block_n;
   int pair;
   int wgrad_pair;
+  int stat_accumulate;
 } dg_conv_opts;
 int dg_conv_opts_check(const dg_conv_opts* opts); /* 0 if the options are well-formed */
 /* nn.Conv2d(ci,co,4,2,1,bias=False) forward, model.py:11-31,84-103 (cuDNN fprop in the reference) */
@@ -138,6 +143,18 @@ int dg_bn_eval_coeffs(const float* gamma, const float* beta, const float* runnin
                       float eps, int C, float* stats, dg_stream_t stream);
 int dg_bn_act_fwd(const void* z, void* y, long long P, int C, const float* stats, int act, float slope,
                   dg_stream_t stream);
+/* folded finalize (two launches fewer per BatchNorm layer and pass): reductions add into ONE zero-initialised
+ * accumulator pair per layer -- acc = float[2*C] -- and the consumer derives its coefficients from the sums itself.
+ * Producers: the *_stats convolutions with dg_conv_opts.stat_accumulate = 1, or dg_bn_stats_acc (sums of a bf16 tensor).
+ * dg_bn_act_fwd_acc also writes stats[4*C] and updates the running statistics; dg_bn_act_bwd_acc (acc2 = float[2*C],
+ * zeroed) writes dz and dgamma / dbeta (both may be NULL).  Summation order of the atomics is not reproducible. */
+int dg_bn_stats_acc(const void* z, long long P, int C, float* acc, dg_stream_t stream);
+int dg_bn_act_fwd_acc(const void* z, void* y, long long P, int C, const float* acc, const float* gamma, const float* beta,
+                      float eps, float momentum, float* stats, float* running_mean, float* running_var, int act,
+                      float slope, dg_stream_t stream);
+int dg_bn_act_bwd_acc(const void* dy, const void* dy2, const float* bcast, float bcast_coef, long long bcast_rows,
+                      const void* z, const float* stats, const float* gamma, long long P, int C, int act, float slope,
+                      float* dgamma, float* dbeta, float grad_beta, void* dz, float* acc2, dg_stream_t stream);
 int dg_bn_act_bwd(const void* dy, const void* dy2, const float* bcast, float bcast_coef, long long bcast_rows,
                   const void* y, const void* z, const float* stats, const float* gamma, long long P, int C, int act,
                   float slope, float* dgamma, float* dbeta, float grad_beta, void* dz, float* coefs, float* scratch,

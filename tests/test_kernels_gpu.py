@@ -518,3 +518,72 @@ def test_conv_role_swapped(B, H, Cb, Cs):
         st = ops.bn_stats_finalize(pp, P, g, b)
         ref = ops.bn_stats(zz.view(P, C), g, b)
         assert torch.allclose(st[0], ref[0], atol=3e-3, rtol=1e-2) and torch.allclose(st[1], ref[1], rtol=1e-2)
+
+
+@pytest.mark.parametrize("P,C,act", [(64 * 16 * 16, 128, 1), (37, 256, 2), (8, 100, 1), (64 * 32 * 32, 64, 2), (4 * 16, 2048, 2)])
+def test_bn_folded_finalize_matches_three_launch_path(P, C, act):
+    """dg_bn_stats_acc + dg_bn_act_fwd_acc / dg_bn_act_bwd_acc (accumulators + coefficients derived in the consumer)
+    against the partial-rows + finalize path: same statistics, outputs, running statistics and gradients."""
+    ops = ops_mod()
+    g = torch.Generator(device="cuda").manual_seed(P + C)
+    z = (torch.randn(P, C, device="cuda", generator=g) * 1.5 + 0.3).to(BF16)
+    dy = (torch.randn(P, C, device="cuda", generator=g) * 0.01).to(BF16)
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g) * 0.1
+    rm1, rv1 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    rm2, rv2 = rm1.clone(), rv1.clone()
+    ctx = ops.OpsContext()
+    with ops.use_context(ctx):
+        ctx.fold_stats = False
+        st_ref = ops.bn_stats(z, gamma, beta, rm1, rv1)
+        y_ref = ops.bn_act_fwd(z, st_ref, act, 0.2)
+        dg_ref, db_ref = torch.full((C,), 2.0, device="cuda"), torch.full((C,), -1.0, device="cuda")
+        dz_ref = ops.bn_act_bwd(dy, y_ref, z, st_ref, gamma, act, 0.2, dg_ref, db_ref, 1.0)
+        ctx.fold_stats = True
+        acc = ops.bn_stats_acc(z)
+        y, st = ops.bn_act_fwd_acc(z, acc, gamma, beta, act, 0.2, rm2, rv2)
+        dg, db = torch.full((C,), 2.0, device="cuda"), torch.full((C,), -1.0, device="cuda")
+        dz = ops.bn_act_bwd(dy, y, z, st, gamma, act, 0.2, dg, db, 1.0)
+        # a second use after the per-iteration reset sees zeroed accumulators again
+        ctx.arena.reset()
+        acc_b = ops.bn_stats_acc(z)
+        assert acc_b.data_ptr() == acc.data_ptr()
+        y_b, _ = ops.bn_act_fwd_acc(z, acc_b, gamma, beta, act, 0.2)
+    torch.cuda.synchronize()
+    assert torch.allclose(st, st_ref, rtol=2e-5, atol=2e-6)
+    assert torch.allclose(rm2, rm1, rtol=1e-5, atol=1e-7) and torch.allclose(rv2, rv1, rtol=1e-5, atol=1e-7)
+    assert rel_l2(y.float(), y_ref.float()) < 1e-3 and rel_l2(y_b.float(), y_ref.float()) < 1e-3
+    assert rel_l2(dz.float(), dz_ref.float()) < 2e-3
+    assert torch.allclose(dg, dg_ref, rtol=1e-4, atol=1e-5) and torch.allclose(db, db_ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,H,Cb,Cs,splitk", [(2, 8, 64, 128, False), (9, 8, 256, 512, False), (64, 8, 256, 512, True),
+                                              (32, 8, 2048, 2048, True)])
+def test_conv_accumulated_stats(B, H, Cb, Cs, splitk):
+    """Convolutions in accumulator mode (dg_conv_opts.stat_accumulate): the [2, C] sums equal the sums over the per-CTA
+    partial rows -- also for split-K shapes, where the finish kernel produces them."""
+    ops = ops_mod()
+    x = rnd(B, Cb, H, H, seed=1).to(BF16)
+    w = (rnd(Cs, Cb, 4, 4, seed=2) / (4 * Cb ** 0.5)).to(BF16).float()
+    wd, wu = ops.pack_weights(w)
+    xn = to_nhwc_bf16(x.float())
+    s = to_nhwc_bf16(rnd(B, Cs, H // 2, H // 2, seed=3))
+    ctx = ops.OpsContext()
+    with ops.use_context(ctx):
+        if splitk:
+            ops.enable_splitk(xn.device)
+        z, acc = ops.conv_down_acc(xn, wd)
+        zu, accu = ops.conv_up_acc(s, wu)
+        zr, part = ops.conv_down_stats(xn, wd)
+    torch.cuda.synchronize()
+    assert (part is None) == splitk
+    zf = z.float().view(-1, Cs)
+    ref = F.conv2d(x.float(), w, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, Cs)
+    assert rel_l2(zf, ref) < 4e-3
+    assert torch.allclose(acc[0], ref.sum(0), rtol=2e-3, atol=2e-3 * float(ref.abs().sum(0).max()))
+    assert torch.allclose(acc[1], (ref * ref).sum(0), rtol=2e-3)
+    refu = F.conv_transpose2d(to_nchw_f32(s), w, stride=2, padding=1).permute(0, 2, 3, 1).reshape(-1, Cb)
+    assert rel_l2(zu.float().view(-1, Cb), refu) < 4e-3
+    assert torch.allclose(accu[1], (refu * refu).sum(0), rtol=2e-3)
+    if part is not None:
+        assert torch.allclose(acc, part.sum(1), rtol=1e-4, atol=1e-3)
