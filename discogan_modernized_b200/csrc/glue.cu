@@ -980,51 +980,64 @@ fm_partial_kernel(const bf16* __restrict__ real, const bf16* __restrict__ fake, 
                   float* __restrict__ diff, float* __restrict__ part) {
   griddep_launch_dependents();
   griddep_wait();
-  float s = 0.f;
+  // block = 32 element vectors x 8 batch slices: a thread sums (real - fake) over every 8th image, so the batch loop --
+  // pure load latency -- is 8x shorter and 8x more loads are in flight than with one thread per vector (42 -> ~8 us at
+  // 64x64, B = 64); the slices are combined through shared memory
+  __shared__ float sh[8][32][8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long n8 = n >> 3;
   const float invB = 1.f / (float)B;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    float ar[8], af[8];
+  float s = 0.f;
+  for (long long i0 = (long long)blockIdx.x * 32; i0 < n8; i0 += (long long)gridDim.x * 32) {
+    const long long i = i0 + tx;
+    float acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) ar[k] = af[k] = 0.f;
-    int b = 0;
-    for (; b + 3 < B; b += 4) {   // 8 independent 16-byte loads in flight: the batch loop is pure latency otherwise
-      bf16x8 vr[4], vf[4];
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (i < n8) {
+      int b = ty;
+      for (; b + 24 < B; b += 32) {   // 8 independent 16-byte loads in flight
+        bf16x8 vr[4], vf[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        vr[u] = *reinterpret_cast<const bf16x8*>(real + (size_t)(b + u) * n + i * 8);
-        vf[u] = *reinterpret_cast<const bf16x8*>(fake + (size_t)(b + u) * n + i * 8);
+        for (int u = 0; u < 4; ++u) {
+          vr[u] = *reinterpret_cast<const bf16x8*>(real + (size_t)(b + 8 * u) * n + i * 8);
+          vf[u] = *reinterpret_cast<const bf16x8*>(fake + (size_t)(b + 8 * u) * n + i * 8);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float fr[8], ff[8];
+          unpack8(vr[u], fr);
+          unpack8(vf[u], ff);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += fr[k] - ff[k];
+        }
       }
+      for (; b < B; b += 8) {
+        float fr[8], ff[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(real + (size_t)b * n + i * 8), fr);
+        unpack8(*reinterpret_cast<const bf16x8*>(fake + (size_t)b * n + i * 8), ff);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float f[8];
-        unpack8(vr[u], f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ar[k] += f[k];
-        unpack8(vf[u], f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) af[k] += f[k];
+        for (int k = 0; k < 8; ++k) acc[k] += fr[k] - ff[k];
       }
     }
-    for (; b < B; ++b) {
-      float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(real + (size_t)b * n + i * 8), f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) ar[k] += f[k];
-      unpack8(*reinterpret_cast<const bf16x8*>(fake + (size_t)b * n + i * 8), f);
+    for (int k = 0; k < 8; ++k) sh[ty][tx][k] = acc[k];
+    __syncthreads();
+    if (ty == 0 && i < n8) {
+      float d[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) af[k] += f[k];
-    }
-    float d[8];
+      for (int k = 0; k < 8; ++k) {
+        float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      d[k] = (ar[k] - af[k]) * invB;
-      s += d[k] * d[k];
+        for (int j = 0; j < 8; ++j) t += sh[j][tx][k];
+        d[k] = t * invB;
+        s += d[k] * d[k];
+      }
+      if (diff) {
+        *reinterpret_cast<float4*>(diff + i * 8) = make_float4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<float4*>(diff + i * 8 + 4) = make_float4(d[4], d[5], d[6], d[7]);
+      }
     }
-    if (diff) {
-      *reinterpret_cast<float4*>(diff + i * 8) = make_float4(d[0], d[1], d[2], d[3]);
-      *reinterpret_cast<float4*>(diff + i * 8 + 4) = make_float4(d[4], d[5], d[6], d[7]);
-    }
+    __syncthreads();
   }
   s = block_sum_256(s);
   if (threadIdx.x == 0) part[blockIdx.x] = s;
@@ -1477,7 +1490,9 @@ int dg_mse_bwd(const float* a, const float* b, long long n, float g, float* da, 
 int dg_fm_fwd(const void* real, const void* fake, int B, long long n, float* diff, float* out, int accumulate,
               float* scratch, cudaStream_t stream) {
   DG_CHECK_ARG(B > 0 && n > 0 && n % 8 == 0 && real && fake && out && scratch, "fm_fwd: bad args (n must be a multiple of 8)");
-  const int grid = ew_grid(n / 8, sms());
+  long long blocks = (n / 8 + 31) / 32;
+  if (blocks > (long long)sms() * 8) blocks = (long long)sms() * 8;      // = dg_reduce_scratch_floats()
+  const int grid = (int)blocks;
   dg_launch(fm_partial_kernel, dg_cfg(grid, 256, 0, stream), (const bf16*)real, (const bf16*)fake, B, n, diff, scratch);
   DG_CHECK_LAUNCH("fm_partial");
   dg_launch(sum_finalize_kernel, dg_cfg(1, 32, 0, stream), scratch, grid, 1.0 / (double)n, out, accumulate);
