@@ -84,9 +84,12 @@ class OpsContext:
         # BatchNorm statistics from the conv epilogue's fp32 accumulators (shared-memory float atomics: the summation
         # order, hence the last bit, varies from run to run); off = a separate deterministic statistics pass
         self.fuse_stats = os.environ.get("DISCOGAN_B200_FUSE_STATS", "1") != "0"
-        # folded finalize: reductions add into arena accumulators, consumers derive their coefficients (two launches
-        # fewer per BatchNorm layer and pass); off = per-CTA partial rows + finalize kernels
-        self.fold_stats = self.fuse_stats and os.environ.get("DISCOGAN_B200_FOLD_STATS", "1") != "0"
+        # folded finalize (opt-in, DISCOGAN_B200_FOLD_STATS=1): reductions add into arena accumulators, consumers derive
+        # their coefficients -- two launches fewer per BatchNorm layer and pass.  Measured on B200 it does NOT pay: inside a
+        # CUDA graph a finalize kernel costs only ~1.5 us of chain time, while ~148-way same-address red.global.add in the
+        # reductions costs 4-13 us per launch (tools/bn_fold_micro.py; step 1.997 -> 2.086 ms at 64x64).  Default: per-CTA
+        # partial rows + finalize kernels.
+        self.fold_stats = self.fuse_stats and os.environ.get("DISCOGAN_B200_FOLD_STATS", "0") == "1"
         self.arena = StatArena(self)
         self._opts = {}
 
