@@ -53,7 +53,9 @@ def parse_header(text=None):
 class ConvOpts(ctypes.Structure):
     """``dg_conv_opts`` of the header: per-call options of the tensor-core convolutions."""
     _fields_ = [("splitk_ws", ctypes.c_void_p), ("splitk_ws_bytes", ctypes.c_size_t), ("block_n", ctypes.c_int),
-                ("pair", ctypes.c_int), ("wgrad_pair", ctypes.c_int), ("stat_accumulate", ctypes.c_int)]
+                ("pair", ctypes.c_int), ("wgrad_pair", ctypes.c_int), ("stat_accumulate", ctypes.c_int),
+                ("affine_scale", ctypes.c_void_p), ("affine_shift", ctypes.c_void_p), ("affine_act", ctypes.c_int),
+                ("affine_slope", ctypes.c_float)]
 
 
 def source_hash():

@@ -52,6 +52,10 @@ struct ConvGemmParams {
   float mask_slope;
   float* img;         // epilogue "image": 3 real output channels written as fp32 NCHW planes instead of `out`
   int img_sigmoid, img_accumulate;
+  const float* aff_scale;   // eval-mode BatchNorm folded into the epilogue: out = act(acc * aff_scale[n] + aff_shift[n])
+  const float* aff_shift;   // (fp32, then the single bf16 rounding); NULL = off
+  int aff_act;
+  float aff_slope;
   int stat_atomic;    // 1: stat_part is one zero-initialised accumulator row pair [2][N]; CTAs add their sums atomically
   float* stat_part;   // BatchNorm statistics fused in the epilogue: per-CTA partial sums [2][gridDim.x][N] of the fp32
                       // accumulators (sum, sum of squares) over the rows this CTA produced; NULL = off
@@ -403,6 +407,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] *= (m[e] > 0.f ? 1.f : p.mask_slope);
               }
+              if (p.aff_scale) {   // same addresses for every thread of the warp: broadcast loads
+                const int n0 = t.nt * p.block_n + c + 8 * j;
+                const float4 s0 = *reinterpret_cast<const float4*>(p.aff_scale + n0);
+                const float4 s1 = *reinterpret_cast<const float4*>(p.aff_scale + n0 + 4);
+                const float4 h0 = *reinterpret_cast<const float4*>(p.aff_shift + n0);
+                const float4 h1 = *reinterpret_cast<const float4*>(p.aff_shift + n0 + 4);
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = act_fwd(f[e] * sc[e] + sh[e], p.aff_act, p.aff_slope);
+              }
               *reinterpret_cast<bf16x8*>(orow + c + 8 * j) = pack8(f);
             }
           }
@@ -577,6 +592,8 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
     // per-warp transpose tile [32 pixels][32 channels] fp32, rows padded to 144 bytes (conflict-free 16-byte reads)
     float* tr = reinterpret_cast<float*>(smem + p.num_stages * stage_bytes + 1024) + (warp - 2) * 32 * kSwapTrStride;
     float ssum = 0.f, ssq = 0.f;
+    const bool aff = p.aff_scale != nullptr;
+    const float asc = (aff && ch < p.N) ? p.aff_scale[ch] : 1.f, ash = (aff && ch < p.N) ? p.aff_shift[ch] : 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -635,7 +652,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
           const float v = __uint_as_float(r[e]);
           ssum += v;            // rows beyond the batch are exact zeros (TMA zero fill)
           ssq += v * v;
-          if (ch_ok) tr[e * kSwapTrStride + lane] = v;
+          if (ch_ok) tr[e * kSwapTrStride + lane] = aff ? act_fwd(v * asc + ash, p.aff_act, p.aff_slope) : v;
         }
         __syncwarp();
         // (2) this thread's pixel, the warp's 32 (16) channels -> 16-byte vector stores
@@ -687,15 +704,23 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
   }
 }
 
-// split-K finish: fp32 workspace -> bf16 output (8 elements per thread)
+// split-K finish: fp32 workspace -> bf16 output (8 elements per thread), optionally through the folded eval-mode
+// BatchNorm affine + activation (channel = element index mod N)
 __global__ void __launch_bounds__(256)
-splitk_finish_kernel(const float* __restrict__ ws, bf16* __restrict__ out, long long n8) {
+splitk_finish_kernel(const float* __restrict__ ws, bf16* __restrict__ out, long long n8, int N,
+                     const float* __restrict__ aff_scale, const float* __restrict__ aff_shift, int aff_act,
+                     float aff_slope) {
   griddep_launch_dependents();
   griddep_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = *reinterpret_cast<const float4*>(ws + i * 8);
     const float4 b = *reinterpret_cast<const float4*>(ws + i * 8 + 4);
-    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (aff_scale) {
+      const int n0 = (int)((i * 8) % N);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = act_fwd(f[e] * aff_scale[n0 + e] + aff_shift[n0 + e], aff_act, aff_slope);
+    }
     *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(f);
   }
 }
@@ -1221,6 +1246,10 @@ struct ConvGemmExtras {
   float mask_slope = 0.f;
   float* img = nullptr;  // when set: Cb (mode 1 output channels) is the padded 16 and only 3 planes are written
   int img_sigmoid = 0, img_accumulate = 0;
+  const float* aff_scale = nullptr;   // folded eval-mode BatchNorm: out = act(acc * scale[n] + shift[n])
+  const float* aff_shift = nullptr;
+  int aff_act = 0;
+  float aff_slope = 0.f;
   float* stat_part = nullptr;  // [2][grid][N] partial BatchNorm sums, or (stat_atomic) [2][N] zero-initialised accumulators
   int stat_atomic = 0;
   int* grid_out = nullptr;     // plan query: receives the grid size, nothing is launched
@@ -1325,6 +1354,12 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   p.img_accumulate = ex.img_accumulate;
   p.stat_part = ex.stat_part;
   p.stat_atomic = ex.stat_atomic;
+  DG_CHECK_ARG(!ex.aff_scale || (ex.aff_shift && !ex.mask && !img_mode && !ex.stat_part),
+               "conv gemm: the folded affine epilogue excludes mask / image / statistics epilogues");
+  p.aff_scale = ex.aff_scale;     // split-K tiles go to the workspace raw: the finish kernel applies the affine
+  p.aff_shift = ex.aff_shift;
+  p.aff_act = ex.aff_act;
+  p.aff_slope = ex.aff_slope;
   // split-K for big GEMMs that would leave most SMs idle (M = B*Hs*Ws small, K = taps*Ck large): partial tiles are
   // accumulated in an fp32 workspace and converted afterwards; such launches cannot fuse the BatchNorm statistics
   p.splits = 1;
@@ -1378,6 +1413,7 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     DG_CHECK_ARG(ex.stat_part == nullptr || ex.stat_atomic, "conv gemm: fused statistics requested for a split-K shape");
     splitk_acc = ex.stat_part;      // accumulator mode: the finish kernel sums the fp32 values it converts
     p.stat_part = nullptr;
+    p.aff_scale = p.aff_shift = nullptr;
     cudaMemsetAsync(p.ws, 0, ws_need, stream);
   }
   const int stage_bytes = use_swap ? 2 * kATileBytes + N * 128 : kATileBytes + (bn / ncta) * 128;
@@ -1433,7 +1469,8 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
       if (sb < 1) sb = 1;
       dg_launch(splitk_finish_stats_kernel, dg_cfg((int)sb, 256, 0, stream), (const float*)p.ws, p.out, rows, N, splitk_acc);
     } else {
-      dg_launch(splitk_finish_kernel, dg_cfg((int)blocks, 256, 0, stream), p.ws, p.out, n8);
+      dg_launch(splitk_finish_kernel, dg_cfg((int)blocks, 256, 0, stream), (const float*)p.ws, p.out, n8, N, ex.aff_scale,
+                ex.aff_shift, ex.aff_act, ex.aff_slope);
     }
     DG_CHECK_LAUNCH("splitk_finish_kernel");
   }
@@ -1474,6 +1511,10 @@ static ConvGemmExtras extras_from(const dg_conv_opts* o) {
     ex.force_bn = o->block_n;
     ex.force_pair = o->pair;
     ex.stat_atomic = o->stat_accumulate;
+    ex.aff_scale = o->affine_scale;
+    ex.aff_shift = o->affine_scale ? o->affine_shift : nullptr;
+    ex.aff_act = o->affine_act;
+    ex.aff_slope = o->affine_slope;
   }
   return ex;
 }
@@ -1488,6 +1529,9 @@ int dg_conv_opts_check(const dg_conv_opts* o) {
                o->pair, o->wgrad_pair);
   DG_CHECK_ARG(((uintptr_t)o->splitk_ws & 15) == 0, "conv opts: split-K workspace must be 16-byte aligned");
   DG_CHECK_ARG(o->stat_accumulate == 0 || o->stat_accumulate == 1, "conv opts: stat_accumulate=%d", o->stat_accumulate);
+  DG_CHECK_ARG(!o->affine_scale || (o->affine_shift && o->affine_act >= 0 && o->affine_act <= 2 &&
+                                    (((uintptr_t)o->affine_scale | (uintptr_t)o->affine_shift) & 15) == 0),
+               "conv opts: affine epilogue needs 16-byte aligned scale and shift vectors and an activation code 0..2");
   return DG_OK;
 }
 

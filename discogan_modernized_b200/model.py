@@ -153,6 +153,17 @@ def _conv_bn(conv_fn, conv_stats_fn, x, w, training):
     return conv_fn(x, w), None
 
 
+def _conv_bn_act(conv_fn, conv_stats_fn, x, w, bn, act, training, bump):
+    """conv -> BatchNorm -> activation.  Returns (z, y, stats); in eval mode with running statistics the BatchNorm affine
+    and the activation are applied inside the conv epilogue (one bf16 rounding, no separate pass): z is None then."""
+    if not training and bn.track_running_stats and ops._conv_impl == "tc" and ops.current().fold_eval_bn:
+        stats = ops.bn_eval_stats(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
+        return None, conv_fn(x, w, affine=(stats, act, LRELU_SLOPE)), stats
+    z, part = _conv_bn(conv_fn, conv_stats_fn, x, w, training)
+    y, stats = _bn_act(z, bn, act, training, part, bump)
+    return z, y, stats
+
+
 def _bn_act(z, bn, act, training, part=None, bump=True):
     """z: NHWC bf16 (any leading dims, channels last); part: partial sums from the producing conv's epilogue.
     Returns (y, stats)."""
@@ -236,8 +247,7 @@ def discriminator_forward(mod, x, save=True):
     for k in range(2, mod.n_down + 1):
         conv, bn = getattr(mod, f"conv{k}"), getattr(mod, f"bn{k}")
         wd, _ = pk.get(conv.weight, True, True)
-        z, part = _conv_bn(ops.conv_down, ops.conv_down_stats, y, wd, training)
-        y, stats = _bn_act(z, bn, ACT_LRELU, training, part, bump)
+        z, y, stats = _conv_bn_act(ops.conv_down, ops.conv_down_stats, y, wd, bn, ACT_LRELU, training, bump)
         ctx.bn.append(_BnSave(z if save else None, y, stats))
         feats.append(y)
     head = getattr(mod, f"conv{mod.n_down + 1}")
@@ -386,8 +396,7 @@ def generator_forward(mod, x, save=True):
     ctx.y1, ctx.enc = y, []
     for conv, bn in zip(enc_convs[1:], enc_bns[1:]):
         wd, _ = pk.get(conv.weight, True, True)
-        z, part = _conv_bn(ops.conv_down, ops.conv_down_stats, y, wd, training)
-        y, stats = _bn_act(z, bn, ACT_LRELU, training, part, bump)
+        z, y, stats = _conv_bn_act(ops.conv_down, ops.conv_down_stats, y, wd, bn, ACT_LRELU, training, bump)
         ctx.enc.append(_BnSave(z if save else None, y, stats))
     # 4x4 valid conv to the 100-d bottleneck (model.py:107-109)
     wd, _ = pk.get(head_conv.weight, True, False)
@@ -403,8 +412,7 @@ def generator_forward(mod, x, save=True):
     ctx.dec = []
     for conv, bn in zip(dec_convs[1:-1], dec_bns[1:]):
         _, wu = pk.get(conv.weight, True, True)
-        z, part = _conv_bn(ops.conv_up, ops.conv_up_stats, y, wu, training)
-        y, stats = _bn_act(z, bn, ACT_RELU, training, part, bump)
+        z, y, stats = _conv_bn_act(ops.conv_up, ops.conv_up_stats, y, wu, bn, ACT_RELU, training, bump)
         ctx.dec.append(_BnSave(z if save else None, y, stats))
     _, wu3 = pk.get_c3(dec_convs[-1].weight)
     out = ops.c3_up_tc(y, wu3, sigmoid=True)

@@ -91,11 +91,14 @@ class OpsContext:
         # partial rows + finalize kernels.
         self.fold_stats = self.fuse_stats and os.environ.get("DISCOGAN_B200_FOLD_STATS", "0") == "1"
         self.arena = StatArena(self)
+        # eval-mode forwards: BatchNorm (running statistics) + activation folded into the producing conv's epilogue
+        self.fold_eval_bn = os.environ.get("DISCOGAN_B200_FOLD_EVAL_BN", "1") != "0"
         self._opts = {}
 
-    def conv_opts(self, device, splitk=True, accumulate=False):
+    def conv_opts(self, device, splitk=True, accumulate=False, affine=None):
         """ctypes ``dg_conv_opts`` for a launch on the current lane (cached per (device, lane): the struct must stay
-        alive until the call returns, and its address is stable for repeated launches)."""
+        alive until the call returns, and its address is stable for repeated launches).  affine = (stats [4,C], act,
+        slope): fold the eval-mode BatchNorm scale / shift and the activation into the epilogue."""
         device = torch.device(device)
         nbytes = self.splitk_bytes.get(device, 0) if splitk else 0
         ptr = 0
@@ -116,6 +119,13 @@ class OpsContext:
         o.splitk_ws, o.splitk_ws_bytes = ptr or None, nbytes
         o.block_n, o.pair, o.wgrad_pair = self.block_n, self.pair, self.wgrad_pair
         o.stat_accumulate = int(accumulate)
+        if affine is not None:
+            stats, act, slope = affine
+            C = stats.shape[1]
+            o.affine_scale, o.affine_shift = stats.data_ptr() + 8 * C, stats.data_ptr() + 12 * C
+            o.affine_act, o.affine_slope = int(act), float(slope)
+        else:
+            o.affine_scale = o.affine_shift = None
         return ctypes.byref(o)
 
     def plan_opts(self, device):
@@ -207,8 +217,8 @@ def enable_splitk(device, nbytes=64 << 20):
     current().splitk_bytes[torch.device(device)] = int(nbytes)
 
 
-def _opts(device, splitk=True, accumulate=False):
-    return current().conv_opts(device, splitk, accumulate)
+def _opts(device, splitk=True, accumulate=False, affine=None):
+    return current().conv_opts(device, splitk, accumulate, affine)
 
 
 # ---- weights / layout ---------------------------------------------------------------------
@@ -254,26 +264,48 @@ def set_conv_impl(name):
     _conv_impl = name
 
 
-def conv_down(big, wd):
-    """[B,H,W,Cb] x Wd[Cs,16,Cb] -> [B,H/2,W/2,Cs]  (Conv2d 4x4 s2 p1 forward / ConvTranspose2d dgrad)."""
+def _check_affine(affine, C):
+    stats, act, _ = affine
+    if stats.dtype != F32 or tuple(stats.shape) != (4, C) or not stats.is_contiguous() or C % 4:
+        raise ValueError(f"affine statistics must be contiguous fp32 [4, {C}] with C a multiple of 4")
+    if act not in (ACT_NONE, ACT_LRELU, ACT_RELU):
+        raise ValueError(f"unknown activation code {act}")
+
+
+def conv_down(big, wd, affine=None):
+    """[B,H,W,Cb] x Wd[Cs,16,Cb] -> [B,H/2,W/2,Cs]  (Conv2d 4x4 s2 p1 forward / ConvTranspose2d dgrad).
+    affine = (stats [4,Cs] from bn_eval_stats, act, slope): out = act(conv * scale + shift) in the epilogue (eval-mode
+    BatchNorm + activation folded into the convolution)."""
     B, H, W, Cb = big.shape
     Cs = wd.shape[0]
     out = torch.empty(B, H // 2, W // 2, Cs, dtype=BF16, device=big.device)
+    if affine is not None:
+        _check_affine(affine, Cs)
+        if _conv_impl != "tc":
+            raise KernelError("the folded affine epilogue exists on the tensor-core path only")
     if _conv_impl == "tc":
         check(lib().dg_conv4x4s2_fprop(_ptr(big, BF16, "big"), _ptr(wd, BF16, "wd"), _ptr(out), B, H, W, Cb, Cs,
-                                       _opts(big.device), _stream()), "dg_conv4x4s2_fprop")
+                                       _opts(big.device, affine=affine), _stream()), "dg_conv4x4s2_fprop")
     else:
         check(lib().dg_simt_conv4x4s2_fprop(_ptr(big, BF16, "big"), _ptr(wd, BF16, "wd"), _ptr(out), B, H, W, Cb, Cs,
                                             _stream()), "dg_simt_conv4x4s2_fprop")
     return out
 
 
-def conv_up(small, wu, mask=None, slope=0.2):
+def conv_up(small, wu, mask=None, slope=0.2, affine=None):
     """[B,Hs,Ws,Cs] x Wu[Cb,16,Cs] -> [B,2Hs,2Ws,Cb]  (Conv2d dgrad / ConvTranspose2d 4x4 s2 p1 forward).
-    mask (bf16, output shape): multiply by the LeakyReLU derivative (mask > 0 ? 1 : slope) in the epilogue."""
+    mask (bf16, output shape): multiply by the LeakyReLU derivative (mask > 0 ? 1 : slope) in the epilogue.
+    affine: see conv_down (eval-mode BatchNorm + activation folded into the ConvTranspose2d)."""
     B, Hs, Ws, Cs = small.shape
     Cb = wu.shape[0]
     out = torch.empty(B, 2 * Hs, 2 * Ws, Cb, dtype=BF16, device=small.device)
+    if affine is not None:
+        _check_affine(affine, Cb)
+        if _conv_impl != "tc" or mask is not None:
+            raise KernelError("the folded affine epilogue exists on the tensor-core path only and excludes the mask")
+        check(lib().dg_conv4x4s2_dgrad(_ptr(small, BF16, "small"), _ptr(wu, BF16, "wu"), _ptr(out), B, Hs, Ws, Cs, Cb,
+                                       _opts(small.device, affine=affine), _stream()), "dg_conv4x4s2_dgrad")
+        return out
     if _conv_impl == "tc" and mask is not None:
         check(lib().dg_conv4x4s2_dgrad_masked(_ptr(small, BF16, "small"), _ptr(wu, BF16, "wu"), _ptr(out),
                                               _ptr(mask, BF16, "mask"), slope, B, Hs, Ws, Cs, Cb, _opts(small.device),

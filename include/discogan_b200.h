@@ -59,6 +59,10 @@ int dg_nchw_f32_to_nhwc_bf16(const float* x, void* y, int B, int HW, int C, dg_s
  *             dg_bn_stats_finalize); 1 = stat_part is ONE zero-initialised accumulator pair float[2][N] that every CTA
  *             adds its sums to (red.global.add) -- consumed directly by dg_bn_act_fwd_acc, no finalize launch; split-K
  *             shapes are supported in this mode (the split-K finish kernel produces the sums)
+ *   affine_scale / affine_shift / affine_act / affine_slope  (fprop / dgrad entry points) fused epilogue
+ *             out = act(acc * scale[c] + shift[c]) per output channel, applied in fp32 before the single bf16 rounding:
+ *             eval-mode BatchNorm (dg_bn_eval_coeffs gives scale = gamma/sqrt(var+eps), shift = beta - mean*scale) and the
+ *             LeakyReLU / ReLU behind it folded into the convolution, inference.py:149,168-172.  NULL scale = off.
  * Results do not depend on block_n / pair / wgrad_pair (bit-identical except for split-K summation order). */
 typedef struct dg_conv_opts {
   void* splitk_ws;
@@ -67,6 +71,10 @@ typedef struct dg_conv_opts {
   int pair;
   int wgrad_pair;
   int stat_accumulate;
+  const float* affine_scale;
+  const float* affine_shift;
+  int affine_act;
+  float affine_slope;
 } dg_conv_opts;
 int dg_conv_opts_check(const dg_conv_opts* opts); /* 0 if the options are well-formed */
 /* nn.Conv2d(ci,co,4,2,1,bias=False) forward, model.py:11-31,84-103 (cuDNN fprop in the reference) */

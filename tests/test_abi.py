@@ -42,8 +42,8 @@ def test_no_global_setters_in_the_abi():
     m = re.search(r"typedef struct dg_conv_opts \{(.*?)\} dg_conv_opts;", text, flags=re.S)
     fields = [f.strip().split()[-1] for f in m.group(1).split(";") if f.strip()]
     assert fields == [n for n, _ in _lib.ConvOpts._fields_]
-    assert ctypes.sizeof(_lib.ConvOpts) == 32
-    bad = _lib.ConvOpts(None, 0, 77, -1, -1)
+    assert ctypes.sizeof(_lib.ConvOpts) == 56
+    bad = _lib.ConvOpts(None, 0, 77, -1, -1, 0)
     assert _lib.lib().dg_conv_opts_check(ctypes.byref(bad)) != 0
     assert _lib.lib().dg_conv_opts_check(None) == 0
 
@@ -97,6 +97,6 @@ def test_launch_plan_query_without_gpu(built):
     assert 0 < rows(0, 2, 4, 4, 128, 64) <= 8
     # the deepest 512^2 layer at B=32 is SM-starved (4 M tiles x 8 N tiles): with a split-K workspace on offer the plan
     # splits (no fused statistics: 0 rows); without one it does not
-    sk = _lib.ConvOpts(None, 64 << 20, 0, -1, -1)
+    sk = _lib.ConvOpts(None, 64 << 20, 0, -1, -1, 0)
     assert built.dg_conv_stats_rows(0, 32, 4, 4, 2048, 2048, ctypes.byref(sk)) == 0
     assert rows(0, 32, 4, 4, 2048, 2048) > 0

@@ -587,3 +587,42 @@ def test_conv_accumulated_stats(B, H, Cb, Cs, splitk):
     assert torch.allclose(accu[1], (refu * refu).sum(0), rtol=2e-3)
     if part is not None:
         assert torch.allclose(acc, part.sum(1), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,H,Cb,Cs,splitk", [(4, 16, 64, 128, False),     # DOWN N=128 / UP N=64: role-swapped kernel when eligible
+                                              (8, 64, 64, 128, False),     # many tiles: swap kernel for both directions
+                                              (3, 32, 128, 256, False), (9, 8, 256, 512, False),
+                                              (32, 8, 2048, 2048, True)])  # split-K: the finish kernel applies the affine
+def test_conv_folded_eval_batchnorm(B, H, Cb, Cs, splitk):
+    """Eval-mode BatchNorm + activation folded into the conv / convT epilogue (dg_conv_opts.affine_*): against
+    act(BN_eval(conv)) in fp32 torch, and against the unfolded kernel pair."""
+    ops = ops_mod()
+    x = rnd(B, Cb, H, H, seed=1).to(BF16)
+    s_in = rnd(B, Cs, H // 2, H // 2, seed=3).to(BF16)
+    w = (rnd(Cs, Cb, 4, 4, seed=2) / (4 * Cb ** 0.5)).to(BF16).float()
+    wd, wu = ops.pack_weights(w)
+    ctx = ops.OpsContext()
+    with ops.use_context(ctx):
+        if splitk:
+            ops.enable_splitk(x.device)
+        for mode, C, act in (("down", Cs, ops.ACT_LRELU), ("up", Cb, ops.ACT_RELU)):
+            g = torch.Generator(device="cuda").manual_seed(C)
+            gamma, beta = torch.rand(C, device="cuda", generator=g) + 0.5, torch.randn(C, device="cuda", generator=g) * 0.2
+            rm, rv = torch.randn(C, device="cuda", generator=g) * 0.1, torch.rand(C, device="cuda", generator=g) + 0.3
+            stats = ops.bn_eval_stats(gamma, beta, rm, rv)
+            if mode == "down":
+                ref = F.conv2d(x.float(), w, stride=2, padding=1)
+                folded = ops.conv_down(to_nhwc_bf16(x.float()), wd, affine=(stats, act, 0.2))
+                plain = ops.conv_down(to_nhwc_bf16(x.float()), wd)
+            else:
+                ref = F.conv_transpose2d(s_in.float(), w, stride=2, padding=1)
+                folded = ops.conv_up(to_nhwc_bf16(s_in.float()), wu, affine=(stats, act, 0.2))
+                plain = ops.conv_up(to_nhwc_bf16(s_in.float()), wu)
+            ref = F.batch_norm(ref, rm, rv, gamma, beta, False, 0.0, 1e-5)
+            ref = F.leaky_relu(ref, 0.2) if act == ops.ACT_LRELU else F.relu(ref)
+            two_pass = ops.bn_act_fwd(plain.view(-1, C), stats, act, 0.2).view(plain.shape)
+            e_fold, e_two = rel_l2(to_nchw_f32(folded), ref), rel_l2(to_nchw_f32(two_pass), ref)
+            assert e_fold < 4e-3, (mode, e_fold)
+            assert e_fold <= e_two + 1e-4, (mode, e_fold, e_two)      # one rounding instead of two
+    with pytest.raises(ValueError):
+        ops.conv_down(to_nhwc_bf16(x.float()), wd, affine=(torch.zeros(4, Cs + 4, device="cuda"), 1, 0.2))

@@ -103,6 +103,33 @@ def test_generator_eval_and_nograd():
     assert int(new.encoder[3].num_batches_tracked) == 1
 
 
+def test_eval_forward_folded_batchnorm_matches_unfolded():
+    """Eval-mode forwards fold BatchNorm + activation into the conv epilogues (default); same result as the separate
+    BatchNorm pass up to one bf16 rounding per layer, both closer than 5e-2 to the oracle."""
+    from discogan_modernized_b200 import ops
+    for kind in ("G", "D"):
+        ref, new = make_pair(kind, 64)
+        x = torch.rand(6, 3, 64, 64, device="cuda")
+        with torch.no_grad():
+            ref(x); new(x)                      # one train-mode pass: running statistics away from their defaults
+        ref.eval(); new.eval()
+        outs = {}
+        for fold in (True, False):
+            ctx = ops.OpsContext()
+            ctx.fold_eval_bn = fold
+            with ops.use_context(ctx), torch.no_grad():
+                outs[fold] = new(x)
+        with torch.no_grad():
+            want = ref(x)
+        if kind == "G":
+            assert rel_l2(outs[True], want) < 5e-2 and rel_l2(outs[False], want) < 5e-2
+            assert rel_l2(outs[True], outs[False]) < 2e-2
+        else:
+            assert torch.allclose(outs[True][0], want[0], atol=3e-2) and torch.allclose(outs[True][0], outs[False][0], atol=2e-2)
+            for a, b, c in zip(outs[True][1], outs[False][1], want[1]):
+                assert rel_l2(a, c) < 5e-2 and rel_l2(a, b) < 2e-2
+
+
 def test_error_behaviour():
     from discogan_modernized_b200 import model
     D = model.Discriminator(64).cuda()
