@@ -116,16 +116,20 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Activations are evaluated branch-free: negative-side slope = slope (LeakyReLU), 0 (ReLU) or 1 (none), then ONE select.
+// A switch on the activation code inside the element loops compiles to a uniform branch pair per element (BSSY/BRA.U),
+// which serialises the unrolled loops (it made the role-swapped GEMM epilogue 3x slower).  NaN propagates (NaN > 0 is false).
+__device__ __forceinline__ float act_nslope(int act, float slope) {
+  return act == DG_ACT_LRELU ? slope : (act == DG_ACT_RELU ? 0.f : 1.f);
+}
 __device__ __forceinline__ float act_fwd(float v, int act, float slope) {
-  if (act == DG_ACT_LRELU) return v > 0.f ? v : v * slope;
-  if (act == DG_ACT_RELU) return v > 0.f ? v : 0.f;
-  return v;
+  const float ns = act_nslope(act, slope);
+  return v > 0.f ? v : v * ns;
 }
 // derivative expressed through the post-activation value y (sign(y)==sign(pre))
 __device__ __forceinline__ float act_grad_from_out(float y, int act, float slope) {
-  if (act == DG_ACT_LRELU) return y > 0.f ? 1.f : slope;
-  if (act == DG_ACT_RELU) return y > 0.f ? 1.f : 0.f;
-  return 1.f;
+  const float ns = act_nslope(act, slope);
+  return y > 0.f ? 1.f : ns;
 }
 
 // Eight bf16 values moved as ONE 128-bit access.  (A struct of four __nv_bfloat162 is copied member-wise by nvcc, i.e.

@@ -33,6 +33,13 @@ constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;           // TMEM columns between the two accumulator stages
 constexpr int kMaxStages = 8;
 
+// folded affine + activation, branch-free (see act_fwd in common.cuh): one fma, one select
+__device__ __forceinline__ float affine_nslope(int act, float slope) { return act_nslope(act, slope); }
+__device__ __forceinline__ float affine_act(float v, float sc, float sh, float nslope) {
+  const float t = fmaf(v, sc, sh);
+  return t > 0.f ? t : t * nslope;
+}
+
 struct ConvGemmParams {
   int mode;  // 0 = DOWN, 1 = UP
   int B, Hm, Wm;  // M-side (small tensor) spatial dims
@@ -299,6 +306,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // epilogue: TMEM lane quarter of this warp is (warp % 4)
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const float aff_nslope = affine_nslope(p.aff_act, p.aff_slope);
     int acc = 0;
     uint32_t acc_phase = 0;
     if (p.stat_part) {
@@ -416,7 +424,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = act_fwd(f[e] * sc[e] + sh[e], p.aff_act, p.aff_slope);
+                for (int e = 0; e < 8; ++e) f[e] = affine_act(f[e], sc[e], sh[e], aff_nslope);
               }
               *reinterpret_cast<bf16x8*>(orow + c + 8 * j) = pack8(f);
             }
@@ -593,6 +601,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
     float* tr = reinterpret_cast<float*>(smem + p.num_stages * stage_bytes + 1024) + (warp - 2) * 32 * kSwapTrStride;
     float ssum = 0.f, ssq = 0.f;
     const bool aff = p.aff_scale != nullptr;
+    const float aff_nslope = affine_nslope(p.aff_act, p.aff_slope);
     const float asc = (aff && ch < p.N) ? p.aff_scale[ch] : 1.f, ash = (aff && ch < p.N) ? p.aff_shift[ch] : 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -652,7 +661,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
           const float v = __uint_as_float(r[e]);
           ssum += v;            // rows beyond the batch are exact zeros (TMA zero fill)
           ssq += v * v;
-          if (ch_ok) tr[e * kSwapTrStride + lane] = aff ? act_fwd(v * asc + ash, p.aff_act, p.aff_slope) : v;
+          if (ch_ok) tr[e * kSwapTrStride + lane] = aff ? affine_act(v, asc, ash, aff_nslope) : v;
         }
         __syncwarp();
         // (2) this thread's pixel, the warp's 32 (16) channels -> 16-byte vector stores
@@ -719,7 +728,8 @@ splitk_finish_kernel(const float* __restrict__ ws, bf16* __restrict__ out, long 
     if (aff_scale) {
       const int n0 = (int)((i * 8) % N);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = act_fwd(f[e] * aff_scale[n0 + e] + aff_shift[n0 + e], aff_act, aff_slope);
+      for (int e = 0; e < 8; ++e)
+        f[e] = affine_act(f[e], aff_scale[n0 + e], aff_shift[n0 + e], affine_nslope(aff_act, aff_slope));
     }
     *reinterpret_cast<bf16x8*>(out + i * 8) = pack8(f);
   }
