@@ -481,6 +481,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 constexpr int kSwapN = 256;
 constexpr int kSwapTrStride = 36;   // floats per row of the epilogue transpose tile (32 + 4 padding)
 
+// kAff: folded eval-mode BatchNorm epilogue; kStats: BatchNorm sums of the accumulators.  Compile-time switches: this
+// kernel's epilogue (TMEM -> smem transpose -> 16-byte stores) is its bottleneck for N = 64, and every instruction added
+// to the per-element loop shows (a run-time select between v and act(v*sc+sh) cost the training path 25-60 %).
+template <bool kAff, bool kStats>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_constant__ CUtensorMap tmW,
                       const ConvGemmParams p) {
@@ -600,9 +604,8 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
     // per-warp transpose tile [32 pixels][32 channels] fp32, rows padded to 144 bytes (conflict-free 16-byte reads)
     float* tr = reinterpret_cast<float*>(smem + p.num_stages * stage_bytes + 1024) + (warp - 2) * 32 * kSwapTrStride;
     float ssum = 0.f, ssq = 0.f;
-    const bool aff = p.aff_scale != nullptr;
     const float aff_nslope = affine_nslope(p.aff_act, p.aff_slope);
-    const float asc = (aff && ch < p.N) ? p.aff_scale[ch] : 1.f, ash = (aff && ch < p.N) ? p.aff_shift[ch] : 0.f;
+    const float asc = (kAff && ch < p.N) ? p.aff_scale[ch] : 1.f, ash = (kAff && ch < p.N) ? p.aff_shift[ch] : 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -659,9 +662,11 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const float v = __uint_as_float(r[e]);
-          ssum += v;            // rows beyond the batch are exact zeros (TMA zero fill)
-          ssq += v * v;
-          if (ch_ok) tr[e * kSwapTrStride + lane] = aff ? affine_act(v, asc, ash, aff_nslope) : v;
+          if (kStats) {
+            ssum += v;          // rows beyond the batch are exact zeros (TMA zero fill)
+            ssq += v * v;
+          }
+          if (ch_ok) tr[e * kSwapTrStride + lane] = kAff ? affine_act(v, asc, ash, aff_nslope) : v;
         }
         __syncwarp();
         // (2) this thread's pixel, the warp's 32 (16) channels -> 16-byte vector stores
@@ -694,7 +699,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmPix, const __grid_co
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (p.stat_part && ch_ok) {
+    if (kStats && p.stat_part && ch_ok) {
       if (p.stat_atomic) {
         atomicAdd(p.stat_part + ch, ssum);
         atomicAdd(p.stat_part + p.N + ch, ssq);
@@ -1453,7 +1458,11 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_gemm_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      e = cudaFuncSetAttribute(conv_gemm_swap_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gemm_swap_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gemm_swap_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       dg_set_error("conv gemm: cannot raise dynamic smem: %s", cudaGetErrorString(e));
       return DG_ERR_CUDA;
@@ -1461,7 +1470,14 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
     attr_set = true;
   }
   if (use_swap)
-    dg_launch(conv_gemm_swap_kernel, dg_cfg(grid, kThreads, smem_bytes, stream), tmA, tmB, p);
+  {
+    if (p.aff_scale)
+      dg_launch(conv_gemm_swap_kernel<true, false>, dg_cfg(grid, kThreads, smem_bytes, stream), tmA, tmB, p);
+    else if (p.stat_part)
+      dg_launch(conv_gemm_swap_kernel<false, true>, dg_cfg(grid, kThreads, smem_bytes, stream), tmA, tmB, p);
+    else
+      dg_launch(conv_gemm_swap_kernel<false, false>, dg_cfg(grid, kThreads, smem_bytes, stream), tmA, tmB, p);
+  }
   else if (ncta == 2)
     dg_launch(conv_gemm_kernel<2>, dg_cfg(grid, kThreads, smem_bytes, stream, 2), tmA, tmB, p);
   else
