@@ -101,15 +101,44 @@ def _new_packed():
 
 
 def _grad_buf(p):
-    """(fp32 gradient buffer of a parameter, beta): the kernels compute grad = beta*grad + new.  A missing buffer is
-    allocated zeroed (beta 1, autograd's accumulate semantics).  The fused trainer marks its flat gradient views
-    ``_dg_fresh`` instead of zero-filling them: the first write of an iteration then overwrites (beta 0)."""
+    """(fp32 gradient buffer of a parameter, beta): the kernels compute grad = beta*grad + new.
+    * inside an ``autograd.Function`` backward (module-level API) the parameter carries ``_dg_out``, a private buffer the
+      Function returns to autograd -- so ``torch.autograd.grad``, parameter hooks and DDP see ordinary gradients;
+    * the fused trainer marks its flat gradient views ``_dg_fresh`` instead of zero-filling them: the first write of an
+      iteration then overwrites (beta 0);
+    * otherwise a missing ``p.grad`` is allocated zeroed (beta 1, accumulate semantics)."""
+    out = getattr(p, "_dg_out", None)
+    if out is not None:
+        if out[1]:
+            out[1] = False
+            return out[0], 0.0
+        return out[0], 1.0
     if getattr(p, "_dg_fresh", False) and p.grad is not None:
         p._dg_fresh = False
         return p.grad, 0.0
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
     return p.grad, 1.0
+
+
+def _with_param_outputs(mod, needs, need_wgrad, run):
+    """Run a backward engine with every parameter's gradient directed into a private buffer and hand those buffers back
+    as the ``autograd.Function``'s parameter gradients (None where autograd did not ask).  The engines write all
+    parameters of a network whenever they write any."""
+    params = list(mod.parameters())
+    if not need_wgrad:
+        return run(), (None,) * len(params)
+    for p in params:
+        p._dg_out = [torch.empty_like(p, memory_format=torch.contiguous_format), True]
+    try:
+        dx = run()
+        if any(p._dg_out[1] for p in params):      # never written: would hand uninitialised memory to autograd
+            raise RuntimeError("internal error: a parameter gradient was not produced by the backward engine")
+        grads = tuple(p._dg_out[0] if need else None for p, need in zip(params, needs))
+    finally:
+        for p in params:
+            p._dg_out = None
+    return dx, grads
 
 
 def _check_input(x, image_size, training):
@@ -325,8 +354,9 @@ class _DiscFn(torch.autograd.Function):
                 dfs.append(ops.nchw_f32_to_nhwc(g.float().contiguous()))
         need_dx = ctx.needs_input_grad[1]
         need_wgrad = any(ctx.needs_input_grad[2:])
-        dx = discriminator_backward(mod, sv, dlogit, dfs, None, need_dx, need_wgrad)
-        return (None, dx) + (None,) * (len(ctx.needs_input_grad) - 2)
+        dx, pgrads = _with_param_outputs(mod, ctx.needs_input_grad[2:], need_wgrad,
+                                         lambda: discriminator_backward(mod, sv, dlogit, dfs, None, need_dx, need_wgrad))
+        return (None, dx) + pgrads
 
 
 class Discriminator(nn.Module):
@@ -497,8 +527,9 @@ class _GenFn(torch.autograd.Function):
             raise RuntimeError("backward through eval-mode BatchNorm is not supported by the B200 kernels")
         need_dx = ctx.needs_input_grad[1]
         need_wgrad = any(ctx.needs_input_grad[2:])
-        dx = generator_backward(mod, ctx.sv, dout.float(), need_dx, need_wgrad)
-        return (None, dx) + (None,) * (len(ctx.needs_input_grad) - 2)
+        dx, pgrads = _with_param_outputs(mod, ctx.needs_input_grad[2:], need_wgrad,
+                                         lambda: generator_backward(mod, ctx.sv, dout.float(), need_dx, need_wgrad))
+        return (None, dx) + pgrads
 
 
 class Generator(nn.Module):

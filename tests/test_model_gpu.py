@@ -103,6 +103,35 @@ def test_generator_eval_and_nograd():
     assert int(new.encoder[3].num_batches_tracked) == 1
 
 
+def test_module_gradients_are_ordinary_autograd_gradients():
+    """torch.autograd.grad w.r.t. parameters, parameter hooks and accumulation over two backward() calls work on the
+    drop-in modules exactly as on the reference modules (the Functions return real parameter gradients)."""
+    ref, new = make_pair("D", 64)
+    x = torch.rand(4, 3, 64, 64, device="cuda")
+    loss = lambda net: net(x)[0].log().mean()
+    want = torch.autograd.grad(loss(ref), [ref.conv3.weight, ref.bn2.bias])
+    got = torch.autograd.grad(loss(new), [new.conv3.weight, new.bn2.bias])
+    for a, b in zip(got, want):
+        assert a is not None and cos(a, b) > 0.95
+    assert new.conv3.weight.grad is None                     # autograd.grad does not touch .grad
+    seen = []
+    h = new.conv2.weight.register_hook(lambda g: seen.append(g.clone()))
+    loss(new).backward()
+    g1 = new.conv2.weight.grad.clone()
+    assert len(seen) == 1 and torch.equal(seen[0], g1)
+    loss(new).backward()                                     # second call accumulates
+    assert rel_l2(new.conv2.weight.grad, 2 * g1) < 2e-2
+    h.remove()
+    new.zero_grad(set_to_none=True)
+    assert all(p.grad is None for p in new.parameters())
+    # only the input gradient requested: no parameter buffers are produced
+    xin = x.clone().requires_grad_(True)
+    for p in new.parameters():
+        p.requires_grad_(False)
+    (gx,) = torch.autograd.grad(new(xin)[0].log().mean(), [xin])
+    assert gx.shape == x.shape and all(p.grad is None for p in new.parameters())
+
+
 def test_eval_forward_folded_batchnorm_matches_unfolded():
     """Eval-mode forwards fold BatchNorm + activation into the conv epilogues (default); same result as the separate
     BatchNorm pass up to one bf16 rounding per layer, both closer than 5e-2 to the oracle."""
