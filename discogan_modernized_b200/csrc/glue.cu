@@ -1509,6 +1509,25 @@ int dg_fm_bwd(const float* diff, int B, long long n, float g, void* dfeat, cudaS
 
 // One Adam step over flat fp32 buffers (n a multiple of 4, 16-byte aligned).  `state` is a device float[4]
 // {steps taken, bias corrections}; zero it once, every call advances it.
+// The two halves of dg_adam_step, for callers that update a parameter buffer piecewise (one call per gradient bucket as its
+// all-reduce completes): dg_adam_tick advances the step count / bias corrections ONCE per optimiser step, dg_adam_apply
+// updates a range with the current state.
+int dg_adam_tick(float* state, float beta1, float beta2, cudaStream_t stream) {
+  DG_CHECK_ARG(state != nullptr, "adam_tick: bad args");
+  dg_launch(adam_tick_kernel, dg_cfg(1, 1, 0, stream), state, beta1, beta2);
+  DG_CHECK_LAUNCH("adam_tick");
+  return DG_OK;
+}
+int dg_adam_apply(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, const float* state, float grad_scale, cudaStream_t stream) {
+  DG_CHECK_ARG(n > 0 && n % 4 == 0 && p && g && m && v && state, "adam_apply: bad args (n must be a multiple of 4)");
+  DG_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam_apply: unaligned buffers");
+  dg_launch(adam_kernel, dg_cfg(ew_grid(n / 4, sms()), 256, 0, stream), (float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, lr,
+                                                         beta1, beta2, eps, weight_decay, state, grad_scale);
+  DG_CHECK_LAUNCH("adam_apply");
+  return DG_OK;
+}
+
 int dg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                  float eps, float weight_decay, float* state, float grad_scale, cudaStream_t stream) {
   DG_CHECK_ARG(n > 0 && n % 4 == 0 && p && g && m && v && state, "adam_step: bad args (n must be a multiple of 4)");

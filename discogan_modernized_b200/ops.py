@@ -693,3 +693,14 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale
     the step count and bias corrections so the call is CUDA-graph replayable)."""
     check(lib().dg_adam_step(_ptr(p, F32, "p"), _ptr(g, F32, "g"), _ptr(m, F32, "m"), _ptr(v, F32, "v"), p.numel(), lr, beta1,
                              beta2, eps, weight_decay, _ptr(state, F32, "state"), grad_scale, _stream()), "dg_adam_step")
+
+
+def adam_tick(state, beta1, beta2):
+    """Advance the device-side Adam step state once (the first half of adam_step)."""
+    check(lib().dg_adam_tick(_ptr(state, F32, "state"), beta1, beta2, _stream()), "dg_adam_tick")
+
+
+def adam_apply(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale=1.0):
+    """Adam update of a (contiguous, 16-byte aligned) range with the current step state (the second half of adam_step)."""
+    check(lib().dg_adam_apply(_ptr(p, F32, "p"), _ptr(g, F32, "g"), _ptr(m, F32, "m"), _ptr(v, F32, "v"), p.numel(), lr, beta1,
+                              beta2, eps, weight_decay, _ptr(state, F32, "state"), grad_scale, _stream()), "dg_adam_apply")

@@ -85,6 +85,14 @@ class FlatNet:
                       self.adam_state, grad_scale)
         self.net._packed.refresh()
 
+    def adam_tick(self, beta1, beta2):
+        """Advance the device-side step state once; ``adam_range`` calls then update pieces of the buffers."""
+        ops.adam_tick(self.adam_state, beta1, beta2)
+
+    def adam_range(self, lo, hi, lr, beta1, beta2, eps, weight_decay, grad_scale):
+        ops.adam_apply(self.flat_p[lo:hi], self.flat_g[lo:hi], self.exp_avg[lo:hi], self.exp_avg_sq[lo:hi], lr, beta1, beta2,
+                       eps, weight_decay, self.adam_state, grad_scale)
+
     @property
     def steps(self):
         return int(self.adam_state[0].item())
@@ -129,6 +137,13 @@ class GradReducer:
         self._pending = []
         self._state = {}         # FlatNet -> dict(buckets, left, passes, slot)
         self.launched = []       # (net numel, lo, hi) of every all-reduce issued (tests / accounting)
+        # on_bucket(flat, lo, hi): called on the bucket's stream right behind its all-reduce (the trainer hangs the Adam
+        # update of that range here); with it set, buckets are tracked even without a process group (world 1)
+        self.on_bucket = None
+
+    @property
+    def active(self):
+        return self.enabled or self.on_bucket is not None
 
     # -- planning -------------------------------------------------------------------------------------
     def _plan(self, flat):
@@ -155,6 +170,9 @@ class GradReducer:
 
     def prepare(self, flat_nets):
         """Create the communicators and bucket plans outside the step (never during CUDA-graph capture)."""
+        if self.active and not self.enabled:
+            for fn in flat_nets:
+                self._plan(fn)
         if not self.enabled:
             return
         for i, fn in enumerate(flat_nets):
@@ -164,18 +182,29 @@ class GradReducer:
                 self._group_for(slot, True)
 
     # -- per-step protocol ----------------------------------------------------------------------------
-    def begin(self, flat, passes, slot=0):
+    def begin(self, flat, passes, slot=0, first=None):
         """Start tracking one stepped network: every parameter will be reported ``passes`` times (once per backward
-        pass of this iteration); its buckets go to communicator ``slot``."""
-        if not self.enabled:
+        pass of this iteration); its buckets go to communicator ``slot``.  ``first()`` runs on the slot's stream ahead of
+        every bucket of this network (the trainer advances the Adam step state there)."""
+        if not self.active:
             return
+        if first is not None:
+            if flat.flat_g.is_cuda:
+                stream = self._streams.get(slot)
+                if stream is None:
+                    stream = self._streams[slot] = torch.cuda.Stream()
+                stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(stream):
+                    first()
+            else:
+                first()
         plan = self._plan(flat)
         self._state[flat] = dict(left=[len(ids) * passes for _, _, ids in plan],
                                  where={pid: b for b, (_, _, ids) in enumerate(plan) for pid in ids}, slot=slot)
 
     def hook(self, flat):
         """The ``grad_ready`` callback for the backward passes of this network (None when not reducing)."""
-        if not self.enabled or flat not in self._state:
+        if not self.active or flat not in self._state:
             return None
         st = self._state[flat]
         plan = flat._buckets
@@ -204,7 +233,10 @@ class GradReducer:
         buf = flat.flat_g[lo:hi]
         self.launched.append((flat.numel, lo, hi))
         if not buf.is_cuda:
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self._group_for(slot, False))
+            if self.enabled:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self._group_for(slot, False))
+            if self.on_bucket is not None:
+                self.on_bucket(flat, lo, hi)
             return
         from . import ops
         stream = self._streams.get(slot)
@@ -222,7 +254,10 @@ class GradReducer:
         with torch.cuda.stream(stream):
             for ev in ready:
                 stream.wait_event(ev)
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self._group_for(slot, True))
+            if self.enabled:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self._group_for(slot, True))
+            if self.on_bucket is not None:
+                self.on_bucket(flat, lo, hi)
             done = torch.cuda.Event()
             done.record(stream)
         self._pending.append(done)
@@ -375,6 +410,11 @@ class DiscoGANTrainer:
         self.G_A, self.G_B, self.D_A, self.D_B = [n.to(self.device).train() for n in nets]
         self.flat = {n: FlatNet(n) for n in (self.G_A, self.G_B, self.D_A, self.D_B)}
         self.reducer = GradReducer(process_group, enabled=data_parallel)
+        # Adam per gradient bucket, right behind the bucket's all-reduce (or, on one GPU, behind the kernels that complete
+        # it): the optimiser overlaps the rest of the backward pass instead of forming a serial tail
+        self.adam_buckets = os.environ.get("DISCOGAN_B200_ADAM_BUCKETS", "1") != "0"
+        if self.adam_buckets:
+            self.reducer.on_bucket = self._adam_bucket
         self.reducer.broadcast_params(self.flat.values())
         self.reducer.prepare(list(self.flat.values()))
         self.loss_buf = torch.zeros(len(LOSS_NAMES), dtype=torch.float32, device=self.device)
@@ -518,13 +558,25 @@ class DiscoGANTrainer:
     def _step_impl(self, A, B, is_dis, rate):
         stepped = self._forward_backward(A, B, is_dis, rate, reduce=True)
         self.reducer.join()
-        self._update(stepped, self.reducer.grad_scale)
+        self._update(stepped, self.reducer.grad_scale, done_in_buckets=self.reducer.active and self.adam_buckets)
 
-    def _update(self, stepped, grad_scale):
+    def _tick(self, net):
+        """The Adam step-state advance of one network, to run ahead of its buckets (None when Adam is not bucketed)."""
+        if not self.adam_buckets:
+            return None
+        return lambda: self.flat[net].adam_tick(self.beta1, self.beta2)
+
+    def _adam_bucket(self, flat, lo, hi):
+        flat.adam_range(lo, hi, self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, self.reducer.grad_scale)
+
+    def _update(self, stepped, grad_scale, done_in_buckets=False):
         self._fork()
         for i, n in enumerate(stepped):
             with self._lane(i):
-                self.flat[n].adam(self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, grad_scale)
+                if done_in_buckets:          # every range was updated behind its bucket: only the bf16 GEMM copies are left
+                    n._packed.refresh()
+                else:
+                    self.flat[n].adam(self.lr, self.beta1, self.beta2, self.eps, self.weight_decay, grad_scale)
         self._join()
 
     def _forward_backward(self, A, B, is_dis, rate, reduce=False):
@@ -560,7 +612,7 @@ class DiscoGANTrainer:
                     self.flat[D].zero_grad()
                     stepped.append(D)
                     if reduce:                   # two backward passes (real, fake) write every parameter
-                        red.begin(self.flat[D], passes=2, slot=slot)
+                        red.begin(self.flat[D], passes=2, slot=slot, first=self._tick(D))
 
         def real_pass(D, img, slot):
             real = discriminator_forward(D, img, save=is_dis)
@@ -624,9 +676,9 @@ class DiscoGANTrainer:
                 n_b = int(co["recon_B"] != 0.0) + int(co["recon_A"] != 0.0 or use_b)
                 n_a = int(co["recon_A"] != 0.0) + int(co["recon_B"] != 0.0 or use_a)
                 if G_B in stepped:
-                    red.begin(self.flat[G_B], passes=n_b, slot=0)
+                    red.begin(self.flat[G_B], passes=n_b, slot=0, first=self._tick(G_B))
                 if G_A in stepped:
-                    red.begin(self.flat[G_A], passes=n_a, slot=1)
+                    red.begin(self.flat[G_A], passes=n_a, slot=1, first=self._tick(G_A))
             hook = (lambda G: red.hook(self.flat[G])) if reduce else (lambda G: None)
             dAB = dBA = dAB_d = dBA_d = None
             fork(6 if small else nb)

@@ -189,6 +189,11 @@ int dg_fm_bwd(const float* diff, int B, long long n, float g, void* dfeat, dg_st
 /* state: device float[4] {steps taken, 1-beta1^t, sqrt(1-beta2^t), -}; zero once, advanced by every call */
 int dg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                  float eps, float weight_decay, float* state, float grad_scale, dg_stream_t stream);
+/* the same in two halves, for piecewise updates (one dg_adam_apply per gradient bucket as its exchange completes):
+ * dg_adam_tick advances the step state once per optimiser step, dg_adam_apply updates a range with the current state */
+int dg_adam_tick(float* state, float beta1, float beta2, dg_stream_t stream);
+int dg_adam_apply(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, const float* state, float grad_scale, dg_stream_t stream);
 
 /* ---- input pipeline: read_images / DiscoGANDataset._load_and_process_image, dataset.py:37-73,238-261 ----
  * One launch preprocesses a batch of decoded uint8 RGB images resident in device memory into the trainer's input layout:

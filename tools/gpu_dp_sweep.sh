@@ -6,7 +6,7 @@ i=0
 while read -r envs; do
   i=$((i+1))
   env $envs timeout -k 5 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700+i)) \
-    bench.py --gpus $N --steps 150 --warmup 15 --no-cpu-baseline --also-512 ${ALSO:-0} > gpurun_out/sweep_$i.log 2> gpurun_out/sweep_$i.err
+    bench.py --gpus $N --steps 120 --warmup 12 --no-cpu-baseline --also-512 ${ALSO:-0} > gpurun_out/sweep_$i.log 2> gpurun_out/sweep_$i.err
   python - <<PY
 import json
 try:
@@ -18,9 +18,8 @@ except Exception as e:
 PY
 done <<LIST
 X=0
-NCCL_MAX_CTAS=8
-NCCL_MAX_CTAS=4
-DISCOGAN_B200_BUCKET_MB=4
-NCCL_MAX_CTAS=8 DISCOGAN_B200_BUCKET_MB=4
-DISCOGAN_B200_DP_COMMS=1
+NCCL_MIN_CTAS=16
+NCCL_MIN_CTAS=32
+NCCL_ALGO=Ring
+NCCL_ALGO=Tree
 LIST
