@@ -38,8 +38,10 @@ def get_gpu_memory(gpu_id):
 def test_batch_size(gpu_id, batch_size, image_size, model_arch="discogan"):
     """One D,G,G cycle at this batch size -> (peak MB used by the step, ok, ms per step)."""
     from .train_step import DiscoGANTrainer
+    import gc
     dev = f"cuda:{gpu_id}"
-    torch.cuda.empty_cache()
+    gc.collect()                                  # garbage from earlier probes would otherwise be freed DURING this probe
+    torch.cuda.empty_cache()                      # and make (peak - base) read low
     torch.cuda.reset_peak_memory_stats(dev)
     base = torch.cuda.memory_allocated(dev)
     tr = None
@@ -56,7 +58,7 @@ def test_batch_size(gpu_id, batch_size, image_size, model_arch="discogan"):
             tr.step(A, B)
         torch.cuda.synchronize(dev)
         ms = (time.perf_counter() - t0) / 3 * 1e3
-        used = (torch.cuda.max_memory_allocated(dev) - base) >> 20
+        used = max(1, (torch.cuda.max_memory_allocated(dev) - base) >> 20)
         return int(used), True, ms
     except (torch.cuda.OutOfMemoryError, RuntimeError) as e:
         if not isinstance(e, torch.cuda.OutOfMemoryError) and "out of memory" not in str(e).lower():

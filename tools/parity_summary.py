@@ -42,7 +42,11 @@ def main(path):
                 out.append(f"| {it} | " + " | ".join(f"{c['kernel'][it][k]:.4f} / {c['bf16e'][it][k]:.4f} / {c['fp32'][it][k]:.4f}" for k in L) + " |")
             out.append("")
         if r["test"] == "accumulated_update":
-            rows = r["rows"]
+            rows = [x for x in r["rows"] if x.get("floor")]
+            if not rows:
+                out += [f"Accumulated update after {r['steps']} steps ({r['S']}x{r['S']}): cos(kernel,bf16e) min "
+                        f"{min(x['cos_bf16e'] for x in r['rows']):.3f}, cos(kernel,fp32) min {min(x['cos_fp32'] for x in r['rows']):.3f}", ""]
+                continue
             out += [f"Accumulated update after {r['steps']} steps ({r['S']}x{r['S']}, {r['variant']} / {r['arch']}): rel(kernel,bf16e)/floor median "
                     f"{statistics.median(x['rel_bf16e'] / x['floor'] for x in rows):.3f}, max {max(x['rel_bf16e'] / x['floor'] for x in rows):.3f}; "
                     f"cos(kernel,fp32) min {min(x['cos_fp32'] for x in rows):.3f}", ""]
