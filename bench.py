@@ -309,8 +309,10 @@ def measure_roofline(tr, batches, torch, pk):
     for n, f in orig.items():
         setattr(ops, n, wrap(n, f, names[n]))
     saved_graphs, saved_side = tr.use_graphs, tr._side  # (_streams() is empty when _side is None)
+    saved_buckets, saved_cb = tr.adam_buckets, tr.reducer.on_bucket
     tr.use_graphs = False                      # per-launch events need eager launches ...
     tr._side = None                            # ... on one stream (no concurrent lane sharing the SMs)
+    tr.adam_buckets, tr.reducer.on_bucket = False, None    # ... and no per-bucket Adam running beside the timed kernels
     try:
         for cycle in range(2):                 # first cycle: untimed, lets the caching allocator grow its eager pool
             recs.clear()                       # (cudaMalloc stalls between the events would be charged to kernels)
@@ -321,6 +323,7 @@ def measure_roofline(tr, batches, torch, pk):
             torch.cuda.synchronize()
     finally:
         tr.use_graphs, tr._side = saved_graphs, saved_side
+        tr.adam_buckets, tr.reducer.on_bucket = saved_buckets, saved_cb
         for n, f in orig.items():
             setattr(ops, n, f)
     # Eager per-launch events include host launch gaps whenever the GPU is faster than Python (always at 64x64).  So the
