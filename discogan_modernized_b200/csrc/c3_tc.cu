@@ -60,7 +60,11 @@ img_pad_nhwc4_kernel(const float* __restrict__ img, const float* __restrict__ im
   }
 }
 
-// w fp32 [64][3][4][4] -> wc bf16 [64][kh*16 + kw*4 + c] (c = 3 zero) and wu3 bf16 [16][tap][64] (rows >= 3 zero)
+// w fp32 [64][3][4][4] -> wc bf16 [64][kh*16 + kw*4 + c] (c = 3 zero) and wu3 bf16 [16][9 shifts][64]: the "up" GEMM
+// computes all four output parities of a pixel at once -- row n = parity * 3 + c (parity = py * 2 + px; rows 12..15 zero),
+// K = (pixel shift (di, dj) in {-1,0,1}^2) x 64 input channels; an entry is W[cs][c][kh][kw] of the tap that parity uses
+// at that shift (py = 0: di 0 -> kh 1, di -1 -> kh 3; py = 1: di +1 -> kh 0, di 0 -> kh 2; same for px / kw) or zero.
+// 9 pixel-tile loads and MMA groups per tile instead of 4 parities x 4 taps = 16.
 __global__ void c3_pack_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wc, bf16* __restrict__ wu3) {
   griddep_launch_dependents();
   griddep_wait();
@@ -71,8 +75,18 @@ __global__ void c3_pack_weights_kernel(const float* __restrict__ w, bf16* __rest
     wc[i] = __float2bfloat16(c < 3 ? w[c64 * 48 + c * 16 + kh * 4 + kw] : 0.f);
   }
   if (wu3 && i < 16 * 16 * 64) {
-    const int cs = i & 63, tap = (i >> 6) & 15, cb = i >> 10;
-    wu3[i] = __float2bfloat16(cb < 3 ? w[cs * 48 + cb * 16 + tap] : 0.f);
+    float v = 0.f;
+    if (i < 16 * 9 * 64) {
+      const int cs = i & 63, shift = (i >> 6) % 9, n = i / (9 * 64);
+      const int par = n / 3, c = n - par * 3;
+      if (par < 4) {
+        const int py = par >> 1, px = par & 1, di = shift / 3 - 1, dj = shift % 3 - 1;
+        const int kh = py == 0 ? (di == 0 ? 1 : (di == -1 ? 3 : -1)) : (di == 1 ? 0 : (di == 0 ? 2 : -1));
+        const int kw = px == 0 ? (dj == 0 ? 1 : (dj == -1 ? 3 : -1)) : (dj == 1 ? 0 : (dj == 0 ? 2 : -1));
+        if (kh >= 0 && kw >= 0) v = w[cs * 48 + c * 16 + kh * 4 + kw];
+      }
+    }
+    wu3[i] = __float2bfloat16(v);
   }
 }
 

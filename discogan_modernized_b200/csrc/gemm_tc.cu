@@ -59,6 +59,7 @@ struct ConvGemmParams {
   float mask_slope;
   float* img;         // epilogue "image": 3 real output channels written as fp32 NCHW planes instead of `out`
   int img_sigmoid, img_accumulate;
+  int img4;           // image mode: one tile covers all four output parities (N = 4 x 3 columns, K = 9 pixel shifts)
   const float* aff_scale;   // eval-mode BatchNorm folded into the epilogue: out = act(acc * aff_scale[n] + aff_shift[n])
   const float* aff_shift;   // (fp32, then the single bf16 rounding); NULL = off
   int aff_act;
@@ -229,6 +230,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (la) tma_load_5d(sa, &tmA, &full_bar[stage], pw * p.Ck + c0, t.w0 + dw, ph, t.h0 + dh, t.b0);
               if (lb) tma_load_2d(sb, &tmB, &full_bar[stage], tap_i * p.Ck + c0, t.nt * p.block_n);
             }
+          } else if (p.img4) {   // all parities at once: K runs over the 3 x 3 pixel shifts (weights packed to match)
+            const int di = tap_i / 3 - 1, dj = tap_i % 3 - 1;
+            if (la) tma_load_4d(sa, &tmA, &full_bar[stage], c0, t.w0 + dj, t.h0 + di, t.b0);
+            if (lb) tma_load_2d(sb, &tmB, &full_bar[stage], tap_i * p.Ck + c0, 0);
           } else {
             const int th = tap_i >> 1, tw = tap_i & 1;
             const int kh = py == 0 ? (th ? 3 : 1) : (th ? 2 : 0);
@@ -367,13 +372,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_wait();
         if (valid) {
           const size_t plane = (size_t)p.Ho * p.Wo;
-          float* o = p.img + (size_t)b * 3 * plane + (size_t)oy * p.Wo + ox;
+          if (p.img4) {   // columns parity * 3 + c of this row = the 2 x 2 output pixels of small pixel (h0 + hl, w0 + wl)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float v = __uint_as_float(r[c]);
-            if (p.img_sigmoid) v = 1.f / (1.f + expf(-v));
-            if (p.img_accumulate) v += o[c * plane];
-            o[c * plane] = v;
+            for (int par = 0; par < 4; ++par) {
+              float* o = p.img + (size_t)b * 3 * plane + (size_t)(2 * (t.h0 + hl) + (par >> 1)) * p.Wo + 2 * (t.w0 + wl) + (par & 1);
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                float v = __uint_as_float(r[par * 3 + c]);
+                if (p.img_sigmoid) v = 1.f / (1.f + expf(-v));
+                if (p.img_accumulate) v += o[c * plane];
+                o[c * plane] = v;
+              }
+            }
+          } else {
+            float* o = p.img + (size_t)b * 3 * plane + (size_t)oy * p.Wo + ox;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float v = __uint_as_float(r[c]);
+              if (p.img_sigmoid) v = 1.f / (1.f + expf(-v));
+              if (p.img_accumulate) v += o[c * plane];
+              o[c * plane] = v;
+            }
           }
         }
       } else {
@@ -1293,8 +1312,9 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   p.N = N;
   p.Ck = mode == 0 ? Cb : Cs;
   p.cpk = p.Ck / 64;
-  p.k_iters = (mode == 0 ? 16 : 4) * p.cpk;
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b * (mode == 0 ? 1 : 4);
+  p.img4 = img_mode ? 1 : 0;   // image mode: all four parities per tile, K over the 3 x 3 pixel shifts (dg_c3_pack_weights)
+  p.k_iters = (mode == 0 ? 16 : (p.img4 ? 9 : 4)) * p.cpk;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b * ((mode == 0 || p.img4) ? 1 : 4);
   // N tile: measured cost of one k-iteration of a 128 x bn x 64 tile is ~{904, 782, 678} cycles for bn = {256, 128, 64}
   // on every layer shape (profiles/README.md), i.e. wide tiles are worth more than filling the last SMs: pick the bn
   // that minimises waves(bn) * cost(bn) on the persistent grid
@@ -1448,7 +1468,7 @@ int launch_conv_gemm(int mode, const void* a, const void* wpacked, void* out, in
   } else {
     rc = make_nhwc_map(&tmA, a, B, Hs, Ws, Cs, p.Wt, p.Ht, p.Bt);
     if (rc) return rc;
-    rc = make_weight_map(&tmB, wpacked, Cb, 16 * Cs, use_swap ? N : bn / ncta);
+    rc = make_weight_map(&tmB, wpacked, Cb, (p.img4 ? 9 : 16) * Cs, use_swap ? N : bn / ncta);
   }
   if (rc) return rc;
   static bool attr_set_dev[kMaxDevices] = {};
