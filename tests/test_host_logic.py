@@ -230,3 +230,24 @@ def test_hyperparameter_search_host_logic(tmp_path):
     s = hs.analyze_results([{"trial_id": 0, "hyperparameters": hps[0], "metrics": m},
                             {"trial_id": 1, "hyperparameters": hps[1], "metrics": {"avg_recon_loss": 0.01}}], tmp_path)
     assert s["best"]["trial_id"] == 1 and (tmp_path / "summary.json").exists()
+
+
+def test_entry_point_flags_and_defaults_match_the_reference(golden_dir):
+    """Entry-point contract: every flag the reference parsers accept is accepted by the
+    re-hosted parsers with the same default -- against tests/golden/ref_cli_defaults.json, minted by
+    oracle/make_cli_golden.py from the reference's own parse_args()."""
+    from discogan_modernized_b200 import angle_pairing, distributed_image_translation, image_translation
+    ref = json.loads((golden_dir / "ref_cli_defaults.json").read_text())
+    for name, mod in (("image_translation", image_translation), ("angle_pairing", angle_pairing),
+                      ("distributed_image_translation", distributed_image_translation)):
+        mine = vars(mod.parse_args([]))
+        for flag, default in ref[name].items():
+            assert flag in mine, (name, flag)
+            assert mine[flag] == default, (name, flag, mine[flag], default)
+    # the log line keeps the reference's field order (image_translation.py:394-398)
+    src = ref["log_line_source"]
+    order = [src.index(k) for k in ("Iter [", "GEN:", "FM:", "RECON:", "DIS:")]
+    assert order == sorted(order)
+    from discogan_modernized_b200.train_step import LOSS_NAMES, format_log_line
+    line = format_log_line(1, 2, {k: 0.0 for k in LOSS_NAMES})
+    assert [line.index(k) for k in ("Iter [", "GEN:", "FM:", "RECON:", "DIS:")] == sorted(line.index(k) for k in ("Iter [", "GEN:", "FM:", "RECON:", "DIS:"))
