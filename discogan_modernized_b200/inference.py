@@ -33,7 +33,9 @@ class GraphedGenerator:
     """Eval-mode generator forward replayed from a CUDA graph (one graph per batch size).  A 64x64 forward is ~35 kernels of
     a few microseconds each: launched one by one from Python it is host-bound (~0.5 ms per batch whatever the batch size);
     replayed it costs what the kernels cost.  The input is copied into a static buffer, the output is a static buffer that
-    the next call with the same batch size overwrites (``translate`` clones what it keeps)."""
+    the next call with the same batch size overwrites (``translate`` clones what it keeps).  The graphs read the bf16
+    GEMM copies of the weights: after changing the generator's parameters (``load_state_dict``, further training) call
+    ``refresh()``, which re-packs them in place; BatchNorm running statistics are read by the replayed kernels directly."""
 
     def __init__(self, generator):
         from . import ops
@@ -43,6 +45,10 @@ class GraphedGenerator:
         self.ctx = ops.OpsContext()
         self._graphs = {}
         self._pool = None
+
+    def refresh(self):
+        """Re-pack the bf16 GEMM weights from the current fp32 parameters (in place: captured graphs stay valid)."""
+        self.g._packed.refresh()
 
     @torch.no_grad()
     def __call__(self, x):

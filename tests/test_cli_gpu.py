@@ -210,5 +210,11 @@ def test_graphed_inference_matches_eager():
     assert torch.equal(gg(x).clone(), want)                              # the first graph is still valid
     out = inference.translate(g, x.cpu(), batch_size=4)                  # 4 + 4 + 1: three graphs, outputs cloned
     assert float((out - want).abs().max()) < 3e-2
+    with torch.no_grad():                                                # new weights: refresh() re-packs in place
+        for p in g.parameters():
+            p.mul_(0.5)
+        gg.refresh()
+        want2 = g(x)
+    assert torch.equal(gg(x).clone(), want2) and not torch.equal(want2, want)
     with pytest.raises(ValueError):
         inference.GraphedGenerator(Generator(True, 64).cuda())     # train mode
